@@ -1,0 +1,275 @@
+"""ctypes binding of include/b3d.h (libb3d.so, sm_100a CUDA kernels).
+
+There is no CPU implementation behind this module: if the library is missing it
+raises, and without a B200-class device every compute call raises ``B3DError``
+(status ``B3D_ERR_NO_DEVICE``), which mirrors the ``std::runtime_error`` the
+reference's GPU entry point throws (src/gpu_impl.cpp:258).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb3d.so")
+
+B3D_OK = 0
+B3D_ERR_NO_DEVICE = -1
+B3D_ERR_CUDA = -2
+B3D_ERR_INVALID = -3
+B3D_ERR_ALLOC = -4
+B3D_ERR_STATE = -5
+NO_MATCH = 0xFFFFFFFF
+
+# every symbol include/b3d.h declares (tests check the library exports exactly these)
+SYMBOLS = [
+    "b3d_cuda_available", "b3d_ctx_create", "b3d_ctx_destroy", "b3d_ctx_set_stream", "b3d_strerror", "b3d_last_error",
+    "b3d_ransac", "b3d_icp",
+    "b3d_set_clouds", "b3d_set_features", "b3d_match_features", "b3d_get_correspondences", "b3d_set_correspondences",
+    "b3d_correspondences_devptr", "b3d_ransac_prepare", "b3d_ransac_score", "b3d_ransac_reduce", "b3d_ransac_finish",
+    "b3d_ransac_counts", "b3d_ransac_hypotheses", "b3d_icp_run", "b3d_icp_nearest",
+    "b3d_kernel_launches", "b3d_stage_ms",
+]
+
+
+class B3DError(RuntimeError):
+    def __init__(self, status: int, msg: str):
+        super().__init__(f"b3d status {status}: {msg}")
+        self.status = status
+
+
+_lib = None
+
+
+def lib():
+    """Load libb3d.so. Fails loudly when the CUDA extension has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing — build it with __graft_entry__.build() "
+                              "(nvcc, sm_100a). There is no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        _declare(L)
+        _lib = L
+    return _lib
+
+
+_vp = C.c_void_p
+_f32p = C.POINTER(C.c_float)
+_i32p = C.POINTER(C.c_int32)
+
+
+def _declare(L):
+    L.b3d_cuda_available.restype = C.c_int
+    L.b3d_ctx_create.argtypes = [C.c_int, C.POINTER(_vp)]
+    L.b3d_ctx_destroy.argtypes = [_vp]
+    L.b3d_ctx_destroy.restype = None
+    L.b3d_ctx_set_stream.argtypes = [_vp, _vp]
+    L.b3d_strerror.argtypes = [C.c_int]
+    L.b3d_strerror.restype = C.c_char_p
+    L.b3d_last_error.argtypes = [_vp]
+    L.b3d_last_error.restype = C.c_char_p
+    L.b3d_ransac.argtypes = [_vp, _vp, C.c_size_t, _vp, C.c_size_t, _vp, _vp, C.c_float, C.c_int, C.c_float,
+                             _f32p, _f32p, _f32p, _i32p]
+    L.b3d_icp.argtypes = [_vp, _vp, C.c_size_t, _vp, _vp, C.c_size_t, _f32p, C.c_float, C.c_int, C.c_int,
+                          _f32p, _f32p, _f32p, _i32p]
+    L.b3d_set_clouds.argtypes = [_vp, _vp, C.c_size_t, _vp, _vp, C.c_size_t, C.c_int]
+    L.b3d_set_features.argtypes = [_vp, _vp, _vp, C.c_int]
+    L.b3d_match_features.argtypes = [_vp, C.c_size_t, C.c_size_t]
+    L.b3d_get_correspondences.argtypes = [_vp, _vp]
+    L.b3d_set_correspondences.argtypes = [_vp, _vp, C.c_int]
+    L.b3d_correspondences_devptr.argtypes = [_vp, C.POINTER(_vp)]
+    L.b3d_ransac_prepare.argtypes = [_vp, C.c_float, C.c_int, C.c_float]
+    L.b3d_ransac_score.argtypes = [_vp, C.c_int, C.c_int]
+    L.b3d_ransac_reduce.argtypes = [_vp, C.c_int, C.c_int, _vp, _vp]
+    L.b3d_ransac_finish.argtypes = [_vp, _vp, _f32p, _f32p, _f32p, _i32p]
+    L.b3d_ransac_counts.argtypes = [_vp, C.c_int, C.c_int, _vp]
+    L.b3d_ransac_hypotheses.argtypes = [_vp, C.c_int, C.c_int, _vp]
+    L.b3d_icp_run.argtypes = [_vp, _f32p, C.c_float, C.c_int, C.c_int, C.c_int, _f32p, _f32p, _f32p, _i32p]
+    L.b3d_icp_nearest.argtypes = [_vp, _f32p, C.c_float, _vp, _vp]
+    L.b3d_kernel_launches.argtypes = [_vp]
+    L.b3d_kernel_launches.restype = C.c_uint64
+    L.b3d_stage_ms.argtypes = [_vp, C.c_int]
+    L.b3d_stage_ms.restype = C.c_float
+
+
+def cuda_available() -> bool:
+    return bool(lib().b3d_cuda_available())
+
+
+def _ptr(a):
+    """Host numpy array / raw integer address / None -> c_void_p."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    return C.c_void_p(a.ctypes.data)
+
+
+def _T_colmajor(T) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(T, np.float32).reshape(4, 4).T).reshape(16)
+
+
+def _T_from_colmajor(buf) -> np.ndarray:
+    return np.asarray(buf, np.float32).reshape(4, 4).T.copy()
+
+
+class Context:
+    """One b3d_ctx: a stream plus persistent device workspace. Not thread-safe; use one per thread."""
+
+    def __init__(self, device: int = 0):
+        self._h = _vp()
+        self._L = lib()
+        rc = self._L.b3d_ctx_create(device, C.byref(self._h))
+        if rc != B3D_OK:
+            raise B3DError(rc, self._L.b3d_strerror(rc).decode())
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._L.b3d_ctx_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc):
+        if rc != B3D_OK:
+            detail = self._L.b3d_last_error(self._h).decode() or self._L.b3d_strerror(rc).decode()
+            raise B3DError(rc, detail)
+
+    # ---- plumbing ----
+    def set_stream(self, cuda_stream: int | None):
+        self._check(self._L.b3d_ctx_set_stream(self._h, _vp(cuda_stream) if cuda_stream else None))
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(self._L.b3d_kernel_launches(self._h))
+
+    def stage_ms(self, stage: int) -> float:
+        return float(self._L.b3d_stage_ms(self._h, stage))
+
+    # ---- whole path ----
+    def ransac(self, src, tgt, src_desc, tgt_desc, voxel_size, max_iterations=100000, confidence=0.999):
+        src = _as_f32(src, 3); tgt = _as_f32(tgt, 3); sd = _as_f32(src_desc, 33); td = _as_f32(tgt_desc, 33)
+        if sd.shape[0] != src.shape[0] or td.shape[0] != tgt.shape[0]:
+            raise ValueError("descriptor rows must match cloud sizes")
+        T = np.empty(16, np.float32); fit = C.c_float(); rm = C.c_float(); best = C.c_int32()
+        self._check(self._L.b3d_ransac(self._h, _ptr(src), src.shape[0], _ptr(tgt), tgt.shape[0], _ptr(sd), _ptr(td),
+                                       voxel_size, max_iterations, confidence,
+                                       T.ctypes.data_as(_f32p), C.byref(fit), C.byref(rm), C.byref(best)))
+        return _T_from_colmajor(T), fit.value, rm.value, best.value
+
+    def icp(self, src, tgt, tgt_normals, T0, distance_threshold, max_iterations=200, point_to_plane=True):
+        src = _as_f32(src, 3); tgt = _as_f32(tgt, 3)
+        nrm = _as_f32(tgt_normals, 3) if tgt_normals is not None else None
+        if nrm is not None and nrm.shape[0] != tgt.shape[0]:
+            nrm = None                      # PointCloud::hasNormals() false, registration.hpp:17
+        T0c = _T_colmajor(T0)
+        T = np.empty(16, np.float32); fit = C.c_float(); rm = C.c_float(); it = C.c_int32()
+        self._check(self._L.b3d_icp(self._h, _ptr(src), src.shape[0], _ptr(tgt), _ptr(nrm), tgt.shape[0],
+                                    T0c.ctypes.data_as(_f32p), distance_threshold, max_iterations, int(bool(point_to_plane)),
+                                    T.ctypes.data_as(_f32p), C.byref(fit), C.byref(rm), C.byref(it)))
+        return _T_from_colmajor(T), fit.value, rm.value, it.value
+
+    # ---- staged ----
+    def set_clouds(self, src, tgt, tgt_normals=None):
+        src = _as_f32(src, 3); tgt = _as_f32(tgt, 3)
+        nrm = _as_f32(tgt_normals, 3) if tgt_normals is not None else None
+        self._keep = (src, tgt, nrm)
+        self._n_src, self._n_tgt = src.shape[0], tgt.shape[0]
+        self._check(self._L.b3d_set_clouds(self._h, _ptr(src), src.shape[0], _ptr(tgt), _ptr(nrm), tgt.shape[0], 0))
+
+    def set_clouds_device(self, src_ptr: int, n_src: int, tgt_ptr: int, nrm_ptr: int | None, n_tgt: int):
+        self._n_src, self._n_tgt = n_src, n_tgt
+        self._check(self._L.b3d_set_clouds(self._h, _vp(src_ptr), n_src, _vp(tgt_ptr), _vp(nrm_ptr) if nrm_ptr else None, n_tgt, 1))
+
+    def set_features(self, src_desc, tgt_desc):
+        sd = _as_f32(src_desc, 33); td = _as_f32(tgt_desc, 33)
+        self._keepf = (sd, td)
+        self._check(self._L.b3d_set_features(self._h, _ptr(sd), _ptr(td), 0))
+
+    def set_features_device(self, sd_ptr: int, td_ptr: int):
+        self._check(self._L.b3d_set_features(self._h, _vp(sd_ptr), _vp(td_ptr), 1))
+
+    def match_features(self, row0=0, row1=None):
+        self._check(self._L.b3d_match_features(self._h, row0, self._n_src if row1 is None else row1))
+
+    def get_correspondences(self) -> np.ndarray:
+        out = np.empty(self._n_src, np.uint32)
+        self._check(self._L.b3d_get_correspondences(self._h, _ptr(out)))
+        return out
+
+    def set_correspondences(self, corr):
+        corr = np.ascontiguousarray(corr, np.uint32)
+        if corr.shape[0] != self._n_src:
+            raise ValueError("correspondences must have one entry per source point")
+        self._check(self._L.b3d_set_correspondences(self._h, _ptr(corr), 0))
+
+    def mark_correspondences_set(self):
+        """After writing into correspondences_devptr() directly (all-gather between ranks)."""
+        self._check(self._L.b3d_set_correspondences(self._h, None, 1))
+
+    def correspondences_devptr(self) -> int:
+        p = _vp()
+        self._check(self._L.b3d_correspondences_devptr(self._h, C.byref(p)))
+        return int(p.value)
+
+    def ransac_prepare(self, voxel_size, max_iterations, confidence):
+        self._H = max_iterations
+        self._check(self._L.b3d_ransac_prepare(self._h, voxel_size, max_iterations, confidence))
+
+    def ransac_score(self, h0=0, h1=None):
+        self._check(self._L.b3d_ransac_score(self._h, h0, self._H if h1 is None else h1))
+
+    def ransac_reduce(self, h0, h1, keys_devptr: int, limit_devptr: int | None = None):
+        self._check(self._L.b3d_ransac_reduce(self._h, h0, h1, _vp(limit_devptr) if limit_devptr else None, _vp(keys_devptr)))
+
+    def ransac_finish(self, keys_devptr: int):
+        T = np.empty(16, np.float32); fit = C.c_float(); rm = C.c_float(); best = C.c_int32()
+        self._check(self._L.b3d_ransac_finish(self._h, _vp(keys_devptr), T.ctypes.data_as(_f32p), C.byref(fit), C.byref(rm), C.byref(best)))
+        return _T_from_colmajor(T), fit.value, rm.value, best.value
+
+    def ransac_counts(self, h0=0, h1=None) -> np.ndarray:
+        h1 = self._H if h1 is None else h1
+        out = np.empty(h1 - h0, np.int32)
+        self._check(self._L.b3d_ransac_counts(self._h, h0, h1, _ptr(out)))
+        return out
+
+    def ransac_hypotheses(self, h0=0, h1=None) -> np.ndarray:
+        h1 = self._H if h1 is None else h1
+        out = np.zeros((h1 - h0, 12), np.float32)
+        self._check(self._L.b3d_ransac_hypotheses(self._h, h0, h1, _ptr(out)))
+        return out
+
+    def icp_run(self, T0, distance_threshold, max_iterations=200, point_to_plane=True, stop_on_convergence=True):
+        T0c = _T_colmajor(T0)
+        T = np.empty(16, np.float32); fit = C.c_float(); rm = C.c_float(); it = C.c_int32()
+        self._check(self._L.b3d_icp_run(self._h, T0c.ctypes.data_as(_f32p), distance_threshold, max_iterations,
+                                        int(bool(point_to_plane)), int(bool(stop_on_convergence)),
+                                        T.ctypes.data_as(_f32p), C.byref(fit), C.byref(rm), C.byref(it)))
+        return _T_from_colmajor(T), fit.value, rm.value, it.value
+
+    def icp_nearest(self, T, distance_threshold):
+        Tc = _T_colmajor(T)
+        idx = np.empty(self._n_src, np.uint32); d2 = np.empty(self._n_src, np.float32)
+        self._check(self._L.b3d_icp_nearest(self._h, Tc.ctypes.data_as(_f32p), distance_threshold, _ptr(idx), _ptr(d2)))
+        return idx, d2
+
+
+def _as_f32(a, cols):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    if a.size == 0:
+        return a.reshape(0, cols)
+    return a.reshape(-1, cols)

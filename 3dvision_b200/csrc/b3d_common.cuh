@@ -1,0 +1,139 @@
+// b3d_common.cuh — context, workspace and launch plumbing shared by the kernels.
+// Host side of the C-ABI in include/b3d.h.  No Eigen, no torch, no CPU compute path.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <random>
+#include <string>
+
+#include "../../include/b3d.h"
+
+namespace b3d {
+
+constexpr int kNumSMs = 148;          // B200: 2 dies x 74 SMs; grids are sized in multiples of this
+constexpr int kDescDim = B3D_DESC_DIM;
+constexpr int kStages = 6;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+    // Grow-only: steady-state calls with non-growing sizes never touch the allocator.
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaError_t e = cudaFree(p); p = nullptr; cap = 0; if (e != cudaSuccess) return e; }
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+// Device-resident scalars shared by the staged kernels (one 256 B block per context).
+struct DeviceState {
+    // RANSAC
+    unsigned long long best_key;      // (fitness_bits << 32) | (0xFFFFFFFF - id); 0 = none
+    unsigned long long exit_key;      // 0xFFFFFFFF - first id with fitness > confidence; 0 = none
+    unsigned int accepted_total;      // accepted RNG draws inside the raw window
+    unsigned int pad0;
+    // ICP
+    float T[16];                      // current transform, column-major
+    float res_T[16];                  // RegistrationResult.transformation
+    float res_fitness, res_rmse;
+    int iterations;                   // iterations applied
+    int done;                         // 1 once converged / broke out
+    int n_corr_last;
+    float out18[20];                  // RANSAC result: T(16), fitness, rmse, best id (as int bits), unused
+};
+
+}  // namespace b3d
+
+struct b3d_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+
+    // resident clouds / features
+    size_t n_src = 0, n_tgt = 0;
+    bool has_normals = false, have_clouds = false, have_feats = false, have_corr = false;
+    b3d::DevBuf stage_a, stage_b, stage_c;   // raw xyz / descriptor staging for H2D
+    b3d::DevBuf src4, tgt4, nrm4;            // float4 SoA-friendly point arrays
+    b3d::DevBuf sdesc, tdesc;                // fp32 descriptors, row-major [n][33]
+    const float* sdesc_p = nullptr;          // where the descriptors actually live (may be caller's device memory)
+    const float* tdesc_p = nullptr;
+    b3d::DevBuf corr;                        // uint32 [n_src]
+
+    // RANSAC
+    std::mt19937 host_rng{42};               // src/registration.cpp:235 — seed is the literal 42
+    size_t raw_have = 0;                     // raw 32-bit outputs cached on device
+    b3d::DevBuf raw;                         // uint32 [raw_have...]
+    b3d::DevBuf draws;                       // uint32 [3*H] accepted index draws
+    b3d::DevBuf scan_tmp;                    // block sums for scans
+    b3d::DevBuf hyp;                         // float [12][H] (SoA): R row-major 9, t 3
+    b3d::DevBuf counts;                      // int32 [H]
+    b3d::DevBuf pairs;                       // float4 [2][n_src]: (s_i, 0), (q_corr[i], 0)
+    b3d::DevBuf seqsum;                      // float scratch for the exact sequential rmse sum
+    int H = 0;
+    float ransac_thr = 0.f, ransac_cut = 0.f, confidence = 0.f;
+    bool prepared = false, scored = false;
+    int scored_lo = 0, scored_hi = 0;
+
+    // ICP
+    b3d::DevBuf grid_slots, grid_cursor, grid_pts, grid_nrm, pt_slot, pt_rank, partials;
+    b3d::DevBuf nn_idx, nn_d2;
+
+    // device scalars + pinned host mirror
+    b3d::DevBuf state;                       // b3d::DeviceState
+    b3d::DeviceState* h_state = nullptr;     // pinned
+
+    cudaEvent_t ev_start[b3d::kStages] = {}, ev_stop[b3d::kStages] = {};
+    bool ev_valid[b3d::kStages] = {};
+};
+
+namespace b3d {
+
+inline int fail_cuda(b3d_ctx* c, cudaError_t e, const char* what, const char* file, int line) {
+    char buf[512];
+    snprintf(buf, sizeof(buf), "%s: %s (%s:%d)", what, cudaGetErrorString(e), file, line);
+    if (c) c->err = buf;
+    return (e == cudaErrorMemoryAllocation) ? B3D_ERR_ALLOC : B3D_ERR_CUDA;
+}
+inline int fail(b3d_ctx* c, int code, const char* msg) { if (c) c->err = msg; return code; }
+
+#define B3D_CUDA(ctx, expr)                                                               \
+    do { cudaError_t _e = (expr); if (_e != cudaSuccess) return b3d::fail_cuda((ctx), _e, #expr, __FILE__, __LINE__); } while (0)
+// kernel launch bookkeeping: count it, then surface launch-configuration errors immediately
+#define B3D_LAUNCHED(ctx)                                                                 \
+    do { (ctx)->launches++; cudaError_t _e = cudaGetLastError();                         \
+         if (_e != cudaSuccess) return b3d::fail_cuda((ctx), _e, "kernel launch", __FILE__, __LINE__); } while (0)
+
+inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
+inline int grid_for(long long work_items, int per_block, int max_waves = 8) {
+    long long blocks = (work_items + per_block - 1) / per_block;
+    if (blocks < 1) blocks = 1;
+    long long cap = (long long)kNumSMs * max_waves;
+    return (int)(blocks < cap ? blocks : cap);
+}
+
+struct StageTimer {
+    b3d_ctx* c; int s;
+    StageTimer(b3d_ctx* ctx, int stage) : c(ctx), s(stage) { cudaEventRecord(c->ev_start[s], c->stream); }
+    ~StageTimer() { cudaEventRecord(c->ev_stop[s], c->stream); c->ev_valid[s] = true; }
+};
+
+// stages implemented in the .cu files
+int match_features_impl(b3d_ctx* c, size_t row0, size_t row1);
+int ransac_prepare_impl(b3d_ctx* c, float voxel, int max_iterations, float confidence);
+int ransac_score_impl(b3d_ctx* c, int h0, int h1);
+int ransac_reduce_impl(b3d_ctx* c, int h0, int h1, const int64_t* limit_key_dev, int64_t* keys_dev);
+int ransac_finish_impl(b3d_ctx* c, const int64_t* keys_dev, float* T, float* fitness, float* rmse, int32_t* best);
+int icp_run_impl(b3d_ctx* c, const float* T0, float thr, int max_iter, int p2plane, int stop_on_conv,
+                 float* T, float* fitness, float* rmse, int32_t* iters);
+int icp_nearest_impl(b3d_ctx* c, const float* T, float thr, uint32_t* idx_host, float* d2_host);
+int xyz_to_float4(b3d_ctx* c, const float* xyz_dev, size_t n, float4* out);
+
+}  // namespace b3d

@@ -1,0 +1,464 @@
+// b3d_icp.cu — point-to-plane / point-to-point ICP on a voxel-hash uniform grid.
+// Replaces Registration::icpRefine (src/registration.cpp:297-414) and the body of
+// GPURegistration::icpRefine (src/gpu_impl.cpp:141-260) of the reference; it is not a
+// port of cuda/icp.cu.  Compile with --fmad=false.
+//
+// Nearest neighbour (registration.cpp:325-338).  The reference scans every target
+// and then discards matches with sqrt(d2) > thr.  A match that survives is therefore
+// within thr of the query, so it is enough to search the 27 cells around the query in
+// a grid whose cell edge is >= 1.02*thr: the result (index and d2 bits) is identical
+// for every point the reference keeps, and points it drops are dropped here too.
+// Ties resolve on (d2, original index), which reproduces the reference's strict '<'
+// scan order independent of the order atomics placed points in their cell.
+//
+// Grid build: cells live in an open-addressing hash table (64-bit packed cell key);
+// points claim a slot with atomicCAS and a rank inside the cell with a
+// warp-aggregated atomicAdd (one atomic per distinct cell per warp); a prefix sum
+// over slot counts gives cell starts; points are then scattered into cell order as
+// float4 (x, y, z, original index) so a cell is one contiguous, vectorised read.
+//
+// Per iteration one fused kernel transforms, searches, thresholds and accumulates the
+// normal equations (or centroid/cross-covariance sums) in fp64 per thread ->
+// warp-shuffle -> block -> per-block partials; a one-block kernel adds the partials
+// in a fixed order (deterministic), solves (6x6 pivoted LDLT or 3x3 Jacobi SVD from
+// b3d_linalg.cuh), updates T and the convergence flag on the device.  Nothing but
+// the final 18 floats crosses PCIe.
+#include "b3d_common.cuh"
+#include "b3d_linalg.cuh"
+#include "b3d_scan.cuh"
+#include <float.h>
+#include <math.h>
+
+namespace b3d {
+
+// ---------------------------------------------------------------------------------
+// voxel-hash grid
+// ---------------------------------------------------------------------------------
+struct __align__(16) CellSlot {
+    unsigned long long key;     // packed cell coordinate, kEmptyKey if unused
+    unsigned start;             // first point of the cell in grid_pts
+    unsigned count;             // points in the cell
+};
+constexpr unsigned long long kEmptyKey = ~0ull;
+constexpr int kCoordBias = 1 << 20;
+constexpr float kCoordLimit = 65536.0f;     // |cell coordinate| bound that keeps fl(p*inv) within 2^-7 cell
+
+struct GridParams {
+    float inv_cell;
+    unsigned mask;              // capacity - 1
+    unsigned max_abs_bits;      // max |coordinate| over the target, as float bits
+    unsigned n_points;
+};
+
+__device__ __forceinline__ int cell_coord(float v, float inv_cell) {
+    float f = floorf(v * inv_cell);
+    f = fminf(fmaxf(f, -(float)(kCoordBias - 2)), (float)(kCoordBias - 2));
+    return (int)f;
+}
+__device__ __forceinline__ unsigned long long pack_cell(int cx, int cy, int cz) {
+    return ((unsigned long long)(unsigned)(cx + kCoordBias) << 42) | ((unsigned long long)(unsigned)(cy + kCoordBias) << 21) |
+           (unsigned long long)(unsigned)(cz + kCoordBias);
+}
+__device__ __forceinline__ unsigned hash_cell(unsigned long long k) {
+    k ^= k >> 33; k *= 0xff51afd7ed558ccdULL; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL; k ^= k >> 33;
+    return (unsigned)k;
+}
+
+__global__ void grid_bounds_kernel(const float4* __restrict__ pts, unsigned n, GridParams* gp) {
+    float m = 0.0f;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float4 p = pts[i];
+        m = fmaxf(m, fmaxf(fabsf(p.x), fmaxf(fabsf(p.y), fabsf(p.z))));
+    }
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));
+    if ((threadIdx.x & 31) == 0 && isfinite(m)) atomicMax(&gp->max_abs_bits, __float_as_uint(m));
+}
+
+__global__ void grid_init_kernel(CellSlot* slots, unsigned capacity, GridParams* gp, float thr, unsigned n_points) {
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < capacity; i += gridDim.x * blockDim.x) {
+        slots[i].key = kEmptyKey; slots[i].start = 0u; slots[i].count = 0u;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        float max_abs = __uint_as_float(gp->max_abs_bits);
+        float cell = thr * 1.02f;
+        float inv = (cell > 0.0f) ? 1.0f / cell : INFINITY;
+        float inv_cap = (max_abs > 0.0f) ? kCoordLimit / max_abs : kCoordLimit;
+        gp->inv_cell = fminf(inv, inv_cap);
+        gp->mask = capacity - 1u;
+        gp->n_points = n_points;
+    }
+}
+
+// claim a slot + a rank inside the cell; one atomicAdd per distinct cell per warp
+__global__ void grid_insert_kernel(const float4* __restrict__ pts, unsigned n, CellSlot* slots, const GridParams* __restrict__ gp,
+                                   unsigned* __restrict__ pt_slot, unsigned* __restrict__ pt_rank) {
+    const float inv = gp->inv_cell; const unsigned mask = gp->mask;
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned total = (n + 31u) & ~31u;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const bool live = i < n;
+        unsigned slot = 0xFFFFFFFFu;
+        if (live) {
+            float4 p = pts[i];
+            unsigned long long key = pack_cell(cell_coord(p.x, inv), cell_coord(p.y, inv), cell_coord(p.z, inv));
+            slot = hash_cell(key) & mask;
+            while (true) {
+                unsigned long long prev = atomicCAS(&slots[slot].key, kEmptyKey, key);
+                if (prev == kEmptyKey || prev == key) break;
+                slot = (slot + 1u) & mask;
+            }
+        }
+        unsigned peers = __match_any_sync(0xffffffffu, slot);
+        unsigned leader = __ffs(peers) - 1u;
+        unsigned base = 0;
+        if (live && lane == leader) base = atomicAdd(&slots[slot].count, (unsigned)__popc(peers));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (live) { pt_slot[i] = slot; pt_rank[i] = base + __popc(peers & ((1u << lane) - 1u)); }
+    }
+}
+
+struct SlotCount { const CellSlot* s; __device__ unsigned operator()(unsigned i) const { return s[i].count; } };
+struct SlotStart { CellSlot* s; __device__ void operator()(unsigned i, unsigned prefix, unsigned) const { s[i].start = prefix; } };
+
+__global__ void grid_scatter_kernel(const float4* __restrict__ pts, const float4* __restrict__ nrm, unsigned n,
+                                    const CellSlot* __restrict__ slots, const unsigned* __restrict__ pt_slot,
+                                    const unsigned* __restrict__ pt_rank, float4* __restrict__ out_pts, float4* __restrict__ out_nrm) {
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        unsigned pos = slots[pt_slot[i]].start + pt_rank[i];
+        float4 p = pts[i]; p.w = __uint_as_float(i);
+        out_pts[pos] = p;
+        if (nrm) out_nrm[pos] = nrm[i];
+    }
+}
+
+// nearest target of p within the 27-cell neighbourhood: lexicographic (d2, index) minimum
+__device__ __forceinline__ void grid_nearest(float px, float py, float pz, const CellSlot* __restrict__ slots,
+                                             const float4* __restrict__ gpts, float inv, unsigned mask,
+                                             float& best_d2, unsigned& best_idx, unsigned& best_pos) {
+    best_d2 = FLT_MAX; best_idx = B3D_NO_MATCH; best_pos = 0u;
+    const int cx = cell_coord(px, inv), cy = cell_coord(py, inv), cz = cell_coord(pz, inv);
+    for (int dz = -1; dz <= 1; ++dz)
+        for (int dy = -1; dy <= 1; ++dy)
+            for (int dx = -1; dx <= 1; ++dx) {
+                const unsigned long long key = pack_cell(cx + dx, cy + dy, cz + dz);
+                unsigned slot = hash_cell(key) & mask;
+                unsigned start = 0, count = 0;
+                while (true) {
+                    const CellSlot s = slots[slot];
+                    if (s.key == key) { start = s.start; count = s.count; break; }
+                    if (s.key == kEmptyKey) break;
+                    slot = (slot + 1u) & mask;
+                }
+                for (unsigned k = 0; k < count; ++k) {
+                    const float4 q = gpts[start + k];
+                    float e0 = px - q.x, e1 = py - q.y, e2 = pz - q.z;
+                    float d2 = e0 * e0 + (e1 * e1 + e2 * e2);          // (p - q).squaredNorm()
+                    unsigned idx = __float_as_uint(q.w);
+                    if (d2 < best_d2 || (d2 == best_d2 && idx < best_idx)) { best_d2 = d2; best_idx = idx; best_pos = start + k; }
+                }
+            }
+}
+
+__device__ __forceinline__ void load_Rt(const float* __restrict__ T, float R[9], float t[3]) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) R[r * 3 + c] = T[c * 4 + r];
+        t[r] = T[12 + r];
+    }
+}
+__device__ __forceinline__ void transform_point(const float R[9], const float t[3], float4 s, float& x, float& y, float& z) {
+    x = (R[0] * s.x + (R[1] * s.y + R[2] * s.z)) + t[0];     // R*s + t, Eigen order (registration.cpp:326)
+    y = (R[3] * s.x + (R[4] * s.y + R[5] * s.z)) + t[1];
+    z = (R[6] * s.x + (R[7] * s.y + R[8] * s.z)) + t[2];
+}
+
+// parity tap: per-source nearest neighbour under T
+__global__ void icp_nearest_kernel(const float4* __restrict__ src, unsigned n_src, const float* __restrict__ T, float thr,
+                                   const CellSlot* __restrict__ slots, const float4* __restrict__ gpts,
+                                   const GridParams* __restrict__ gp, uint32_t* __restrict__ out_idx, float* __restrict__ out_d2) {
+    float R[9], t[3];
+    load_Rt(T, R, t);
+    const float inv = gp->inv_cell; const unsigned mask = gp->mask;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n_src; i += gridDim.x * blockDim.x) {
+        float x, y, z; transform_point(R, t, src[i], x, y, z);
+        float d2; unsigned idx, pos;
+        grid_nearest(x, y, z, slots, gpts, inv, mask, d2, idx, pos);
+        if (idx != B3D_NO_MATCH && sqrtf(d2) > thr) { idx = B3D_NO_MATCH; }
+        out_idx[i] = idx;
+        out_d2[i] = (idx == B3D_NO_MATCH) ? FLT_MAX : d2;
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// fused iteration: transform -> NN -> threshold -> accumulate
+// ---------------------------------------------------------------------------------
+constexpr int kIcpThreads = 256;
+constexpr int kAccPlane = 28;     // 21 (upper ATA) + 6 (ATb) + 1 (sum d2)
+constexpr int kAccPoint = 16;     // 3 (sum p) + 3 (sum q) + 9 (sum p q^T) + 1 (sum d2)
+constexpr int kAccMax = 28;
+constexpr int kPartialStride = 32;   // doubles per block partial: kAccMax values + count
+
+template <int NV>
+__device__ __forceinline__ void block_reduce_store(double (&acc)[NV], int n_corr, double* __restrict__ partial_out) {
+    __shared__ double red[kIcpThreads / 32][kAccMax + 1];
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double cnt = (double)n_corr;
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) acc[v] += __shfl_xor_sync(0xffffffffu, acc[v], s);
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, s);
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) red[warp][v] = acc[v];
+        red[warp][kAccMax] = cnt;
+    }
+    __syncthreads();
+    if (threadIdx.x <= kAccMax) {
+        const int v = threadIdx.x;
+        if (v < NV || v == kAccMax) {
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < kIcpThreads / 32; ++w) s += red[w][v];
+            partial_out[v] = s;
+        }
+    }
+}
+
+template <bool PLANE>
+__global__ void __launch_bounds__(kIcpThreads)
+icp_accumulate_kernel(const float4* __restrict__ src, unsigned n_src, const DeviceState* __restrict__ st, float thr,
+                      const CellSlot* __restrict__ slots, const float4* __restrict__ gpts, const float4* __restrict__ gnrm,
+                      const GridParams* __restrict__ gp, double* __restrict__ partials) {
+    if (st->done) return;
+    float R[9], t[3];
+    load_Rt(st->T, R, t);
+    const float inv = gp->inv_cell; const unsigned mask = gp->mask;
+    constexpr int NV = PLANE ? kAccPlane : kAccPoint;
+    double acc[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) acc[v] = 0.0;
+    int n_corr = 0;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n_src; i += gridDim.x * blockDim.x) {
+        float x, y, z; transform_point(R, t, src[i], x, y, z);
+        float d2; unsigned idx, pos;
+        grid_nearest(x, y, z, slots, gpts, inv, mask, d2, idx, pos);
+        if (idx == B3D_NO_MATCH) continue;
+        if (sqrtf(d2) > thr) continue;                     // registration.cpp:337-338 (d == thr is kept)
+        ++n_corr;
+        const float4 q = gpts[pos];
+        if (PLANE) {
+            const float4 n = gnrm[pos];
+            float J[6];
+            J[0] = y * n.z - z * n.y;                      // p.cross(n), registration.cpp:346
+            J[1] = z * n.x - x * n.z;
+            J[2] = x * n.y - y * n.x;
+            J[3] = n.x; J[4] = n.y; J[5] = n.z;
+            float r = (x - q.x) * n.x + ((y - q.y) * n.y + (z - q.z) * n.z);   // (p - q).dot(n)
+            int k = 0;
+#pragma unroll
+            for (int a = 0; a < 6; ++a)
+#pragma unroll
+                for (int b = a; b < 6; ++b) acc[k++] += (double)(J[a] * J[b]);   // fp32 product, as the reference forms it
+#pragma unroll
+            for (int a = 0; a < 6; ++a) acc[21 + a] += (double)(J[a] * r);
+            acc[27] += (double)d2;
+        } else {
+            acc[0] += (double)x; acc[1] += (double)y; acc[2] += (double)z;
+            acc[3] += (double)q.x; acc[4] += (double)q.y; acc[5] += (double)q.z;
+            const double p[3] = {(double)x, (double)y, (double)z};
+            const double qq[3] = {(double)q.x, (double)q.y, (double)q.z};
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int b = 0; b < 3; ++b) acc[6 + a * 3 + b] += p[a] * qq[b];
+            acc[15] += (double)d2;
+        }
+    }
+    block_reduce_store<NV>(acc, n_corr, partials + (size_t)blockIdx.x * kPartialStride);
+}
+
+// one block: fixed-order sum of the block partials, solve, update T / result / flags
+template <bool PLANE>
+__global__ void __launch_bounds__(64)
+icp_update_kernel(const double* __restrict__ partials, int n_blocks, int iter, float n_src_f, int stop_on_convergence,
+                  DeviceState* __restrict__ st) {
+    if (st->done) return;
+    __shared__ double tot[kPartialStride];
+    const int v = threadIdx.x;
+    if (v < kPartialStride) {
+        double s = 0.0;
+        for (int b = 0; b < n_blocks; ++b) s += partials[(size_t)b * kPartialStride + v];
+        tot[v] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    const int n_corr = (int)(tot[kAccMax] + 0.5);
+    st->n_corr_last = n_corr;
+    if (n_corr < 3) { st->done = 1; return; }              // registration.cpp:361
+    float delta[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) delta[i] = (i % 5 == 0) ? 1.0f : 0.0f;
+    float total_error;
+    if (PLANE) {
+        float A[36], nb[6], x[6];
+        int k = 0;
+        for (int a = 0; a < 6; ++a)
+            for (int b = a; b < 6; ++b) { float val = (float)tot[k++]; A[a * 6 + b] = val; A[b * 6 + a] = val; }
+        for (int a = 0; a < 6; ++a) nb[a] = -(float)tot[21 + a];
+        total_error = (float)tot[27];
+        ldlt6_solve(A, nb, x);                               // registration.cpp:366
+        Mat3 dR; euler_xyz_to_matrix(x[0], x[1], x[2], dR);  // registration.cpp:369-371
+        for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) delta[c * 4 + r] = dR(r, c); delta[12 + r] = x[3 + r]; }
+    } else {
+        const double n = (double)n_corr;
+        double pm[3], qm[3];
+        for (int a = 0; a < 3; ++a) { pm[a] = tot[a] / n; qm[a] = tot[3 + a] / n; }
+        Mat3 H;
+        for (int a = 0; a < 3; ++a)
+            for (int b = 0; b < 3; ++b) H(a, b) = (float)(tot[6 + a * 3 + b] - n * pm[a] * qm[b]);   // sum (p-pm)(q-qm)^T
+        total_error = (float)tot[15];
+        Mat3 dR; rotation_from_cross_covariance(H, dR);      // registration.cpp:388-394
+        float pmf[3] = {(float)pm[0], (float)pm[1], (float)pm[2]}, qmf[3] = {(float)qm[0], (float)qm[1], (float)qm[2]};
+        float r0, r1, r2; mat3_vec(dR, pmf[0], pmf[1], pmf[2], r0, r1, r2);
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) delta[c * 4 + r] = dR(r, c);
+        delta[12] = qmf[0] - r0; delta[13] = qmf[1] - r1; delta[14] = qmf[2] - r2;     // registration.cpp:396
+    }
+    float Tn[16];
+    mat4_mul(delta, st->T, Tn);                              // T = delta * T
+    const float prev_rmse = st->res_rmse;
+    const float rmse = sqrtf(total_error / (float)n_corr);
+    for (int i = 0; i < 16; ++i) { st->T[i] = Tn[i]; st->res_T[i] = Tn[i]; }
+    st->res_rmse = rmse;
+    st->res_fitness = (float)n_corr / n_src_f;
+    st->iterations = iter + 1;
+    if (stop_on_convergence && iter > 0 && fabsf(prev_rmse - rmse) < 1e-6f) st->done = 1;    // registration.cpp:406
+}
+
+__global__ void icp_state_init_kernel(DeviceState* st, const float* __restrict__ T0) {
+    int i = threadIdx.x;
+    if (i < 16) { st->T[i] = T0[i]; st->res_T[i] = T0[i]; }
+    if (i == 0) { st->res_fitness = 0.0f; st->res_rmse = 0.0f; st->iterations = 0; st->done = 0; st->n_corr_last = 0; }
+}
+
+// ---------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------
+static unsigned pow2_at_least(size_t v) { unsigned c = 1024; while ((size_t)c < v) c <<= 1; return c; }
+
+static int build_grid(b3d_ctx* c, float thr, GridParams** gp_out, unsigned* capacity_out) {
+    StageTimer timer(c, 4);
+    const unsigned n = (unsigned)c->n_tgt;
+    const unsigned capacity = pow2_at_least(2 * (size_t)n);
+    B3D_CUDA(c, c->grid_slots.ensure(sizeof(CellSlot) * capacity));
+    B3D_CUDA(c, c->grid_cursor.ensure(sizeof(GridParams)));
+    B3D_CUDA(c, c->grid_pts.ensure(sizeof(float4) * (n ? n : 1)));
+    B3D_CUDA(c, c->grid_nrm.ensure(sizeof(float4) * (n ? n : 1)));
+    B3D_CUDA(c, c->pt_slot.ensure(sizeof(unsigned) * (n ? n : 1)));
+    B3D_CUDA(c, c->pt_rank.ensure(sizeof(unsigned) * (n ? n : 1)));
+    GridParams* gp = c->grid_cursor.as<GridParams>();
+    CellSlot* slots = c->grid_slots.as<CellSlot>();
+    B3D_CUDA(c, cudaMemsetAsync(gp, 0, sizeof(GridParams), c->stream));
+    if (n) { grid_bounds_kernel<<<grid_for(n, 256, 2), 256, 0, c->stream>>>(c->tgt4.as<float4>(), n, gp); B3D_LAUNCHED(c); }
+    grid_init_kernel<<<grid_for(capacity, 256, 4), 256, 0, c->stream>>>(slots, capacity, gp, thr, n);
+    B3D_LAUNCHED(c);
+    if (n) {
+        grid_insert_kernel<<<grid_for(n, 256, 8), 256, 0, c->stream>>>(c->tgt4.as<float4>(), n, slots, gp, c->pt_slot.as<unsigned>(), c->pt_rank.as<unsigned>());
+        B3D_LAUNCHED(c);
+        const unsigned tiles = (unsigned)div_up(capacity, kScanTile);
+        B3D_CUDA(c, c->scan_tmp.ensure(sizeof(unsigned) * (tiles + 1)));
+        SlotCount cnt{slots}; SlotStart st{slots};
+        scan_tile_sums_kernel<<<tiles, kScanThreads, 0, c->stream>>>(cnt, capacity, c->scan_tmp.as<unsigned>());
+        B3D_LAUNCHED(c);
+        scan_tile_offsets_kernel<<<1, kScanThreads, 0, c->stream>>>(c->scan_tmp.as<unsigned>(), tiles, (unsigned*)nullptr);
+        B3D_LAUNCHED(c);
+        scan_emit_kernel<<<tiles, kScanThreads, 0, c->stream>>>(cnt, st, capacity, c->scan_tmp.as<unsigned>());
+        B3D_LAUNCHED(c);
+        grid_scatter_kernel<<<grid_for(n, 256, 8), 256, 0, c->stream>>>(c->tgt4.as<float4>(), c->has_normals ? c->nrm4.as<float4>() : nullptr, n, slots,
+                                                                        c->pt_slot.as<unsigned>(), c->pt_rank.as<unsigned>(),
+                                                                        c->grid_pts.as<float4>(), c->grid_nrm.as<float4>());
+        B3D_LAUNCHED(c);
+    }
+    *gp_out = gp; *capacity_out = capacity;
+    return B3D_OK;
+}
+
+int icp_run_impl(b3d_ctx* c, const float* T0, float thr, int max_iter, int p2plane, int stop_on_conv,
+                 float* T, float* fitness, float* rmse, int32_t* iters) {
+    if (!c->have_clouds) return fail(c, B3D_ERR_STATE, "icp_run: clouds not set");
+    DeviceState* st = c->state.as<DeviceState>();
+    // RegistrationResult starts as {initial_transform, 0, 0} (registration.cpp:309-311)
+    for (int i = 0; i < 16; ++i) T[i] = T0[i];
+    *fitness = 0.0f; *rmse = 0.0f; if (iters) *iters = 0;
+    if (max_iter <= 0 || c->n_src == 0 || c->n_tgt == 0) return B3D_OK;    // n_corr < 3 at iteration 0 => break
+    const bool plane = p2plane && c->has_normals;            // registration.cpp:343
+    GridParams* gp; unsigned capacity;
+    int rc = build_grid(c, thr, &gp, &capacity);
+    if (rc != B3D_OK) return rc;
+
+    for (int i = 0; i < 16; ++i) c->h_state->out18[i] = T0[i];
+    B3D_CUDA(c, cudaMemcpyAsync(st->out18, c->h_state->out18, sizeof(float) * 16, cudaMemcpyHostToDevice, c->stream));
+    icp_state_init_kernel<<<1, 32, 0, c->stream>>>(st, st->out18);
+    B3D_LAUNCHED(c);
+
+    const unsigned n_src = (unsigned)c->n_src;
+    const int blocks = grid_for(n_src, kIcpThreads, 4);
+    B3D_CUDA(c, c->partials.ensure(sizeof(double) * kPartialStride * (size_t)blocks));
+    {
+        StageTimer timer(c, 5);
+        const CellSlot* slots = c->grid_slots.as<CellSlot>();
+        for (int iter = 0; iter < max_iter; ++iter) {
+            if (plane) {
+                icp_accumulate_kernel<true><<<blocks, kIcpThreads, 0, c->stream>>>(c->src4.as<float4>(), n_src, st, thr, slots, c->grid_pts.as<float4>(),
+                                                                                   c->grid_nrm.as<float4>(), gp, c->partials.as<double>());
+                B3D_LAUNCHED(c);
+                icp_update_kernel<true><<<1, 64, 0, c->stream>>>(c->partials.as<double>(), blocks, iter, (float)c->n_src, stop_on_conv, st);
+                B3D_LAUNCHED(c);
+            } else {
+                icp_accumulate_kernel<false><<<blocks, kIcpThreads, 0, c->stream>>>(c->src4.as<float4>(), n_src, st, thr, slots, c->grid_pts.as<float4>(),
+                                                                                    c->grid_nrm.as<float4>(), gp, c->partials.as<double>());
+                B3D_LAUNCHED(c);
+                icp_update_kernel<false><<<1, 64, 0, c->stream>>>(c->partials.as<double>(), blocks, iter, (float)c->n_src, stop_on_conv, st);
+                B3D_LAUNCHED(c);
+            }
+            // poll the device-side done flag now and then so converged runs stop launching
+            if ((iter & 15) == 15 && iter + 1 < max_iter) {
+                B3D_CUDA(c, cudaMemcpyAsync(&c->h_state->done, &st->done, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+                B3D_CUDA(c, cudaStreamSynchronize(c->stream));
+                if (c->h_state->done) break;
+            }
+        }
+    }
+    B3D_CUDA(c, cudaMemcpyAsync(c->h_state, st, sizeof(DeviceState), cudaMemcpyDeviceToHost, c->stream));
+    B3D_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < 16; ++i) T[i] = c->h_state->res_T[i];
+    *fitness = c->h_state->res_fitness; *rmse = c->h_state->res_rmse;
+    if (iters) *iters = c->h_state->iterations;
+    return B3D_OK;
+}
+
+int icp_nearest_impl(b3d_ctx* c, const float* T, float thr, uint32_t* idx_host, float* d2_host) {
+    if (!c->have_clouds) return fail(c, B3D_ERR_STATE, "icp_nearest: clouds not set");
+    if (c->n_src == 0) return B3D_OK;
+    DeviceState* st = c->state.as<DeviceState>();
+    GridParams* gp; unsigned capacity;
+    int rc = build_grid(c, thr, &gp, &capacity);
+    if (rc != B3D_OK) return rc;
+    const unsigned n_src = (unsigned)c->n_src;
+    B3D_CUDA(c, c->nn_idx.ensure(sizeof(uint32_t) * n_src));
+    B3D_CUDA(c, c->nn_d2.ensure(sizeof(float) * n_src));
+    for (int i = 0; i < 16; ++i) c->h_state->out18[i] = T[i];
+    B3D_CUDA(c, cudaMemcpyAsync(st->out18, c->h_state->out18, sizeof(float) * 16, cudaMemcpyHostToDevice, c->stream));
+    icp_nearest_kernel<<<grid_for(n_src, 256, 8), 256, 0, c->stream>>>(c->src4.as<float4>(), n_src, st->out18, thr, c->grid_slots.as<CellSlot>(),
+                                                                       c->grid_pts.as<float4>(), gp, c->nn_idx.as<uint32_t>(), c->nn_d2.as<float>());
+    B3D_LAUNCHED(c);
+    B3D_CUDA(c, cudaMemcpyAsync(idx_host, c->nn_idx.p, sizeof(uint32_t) * n_src, cudaMemcpyDeviceToHost, c->stream));
+    B3D_CUDA(c, cudaMemcpyAsync(d2_host, c->nn_d2.p, sizeof(float) * n_src, cudaMemcpyDeviceToHost, c->stream));
+    B3D_CUDA(c, cudaStreamSynchronize(c->stream));
+    return B3D_OK;
+}
+
+}  // namespace b3d

@@ -1,0 +1,456 @@
+// b3d_ransac.cu — RANSAC hypothesis generation, inlier scoring and best selection.
+// Replaces src/registration.cpp:234-295 of the reference.  Compile with --fmad=false.
+//
+//  * RNG: the reference draws from std::mt19937(42) through
+//    std::uniform_int_distribution<size_t>(0, Ns-1) (registration.cpp:235-239).  The raw
+//    32-bit stream depends only on the literal seed, so it is generated once per
+//    context and kept resident; `raw[j]` is then a counter-based generator.  libstdc++
+//    maps raw -> index with Lemire's multiply-shift + rejection; rejections shift all
+//    later draws, so accepted draws are compacted with a device-wide prefix sum.
+//  * Hypotheses: one thread per hypothesis runs the 3-point Kabsch + Jacobi SVD of
+//    b3d_linalg.cuh and stores (R,t) in SoA form; degenerate triples are marked.
+//  * Scoring (dominant cost, FP32-issue bound): one hypothesis per thread with the
+//    (source, matched target) pair stream broadcast out of shared memory, so every
+//    LDS feeds 27 x KH arithmetic instructions and no cross-lane reduction is needed.
+//    The grid is (hypothesis tiles) x (pair ranges); partial counts meet in integer
+//    atomics, which are exact.  sqrt is monotone, so  sqrt(d2) < thr  is evaluated as
+//    d2 < cut  with cut = the smallest float whose correctly rounded sqrt is >= thr.
+//  * Selection: strict '>' on fitness with earliest id winning, early exit on
+//    fitness > confidence (registration.cpp:284-290) as packed 64-bit max-reductions.
+#include "b3d_common.cuh"
+#include "b3d_linalg.cuh"
+#include "b3d_scan.cuh"
+#include <float.h>
+#include <math.h>
+
+namespace b3d {
+
+// ---------------------------------------------------------------------------------
+// RNG mapping
+// ---------------------------------------------------------------------------------
+struct LemireAccept {
+    const uint32_t* raw; uint32_t range, reject_below;
+    __device__ unsigned operator()(unsigned j) const {
+        uint32_t lo = (uint32_t)((uint64_t)raw[j] * range);
+        return lo >= reject_below ? 1u : 0u;
+    }
+};
+struct DrawEmit {
+    const uint32_t* raw; uint32_t range; uint32_t* draws; unsigned need;
+    __device__ void operator()(unsigned j, unsigned prefix, unsigned accepted) const {
+        if (accepted && prefix < need) draws[prefix] = (uint32_t)(((uint64_t)raw[j] * range) >> 32);
+    }
+};
+
+// ---------------------------------------------------------------------------------
+// pairs[i] = s_i ; pairs[n + i] = q_{corr[i]}
+// ---------------------------------------------------------------------------------
+__global__ void gather_pairs_kernel(const float4* __restrict__ src4, const float4* __restrict__ tgt4,
+                                    const uint32_t* __restrict__ corr, unsigned n, unsigned n_tgt, float4* __restrict__ pairs) {
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        pairs[i] = src4[i];
+        unsigned j = corr[i];
+        pairs[n + i] = (j < n_tgt) ? tgt4[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// hypothesis generation: hyp is SoA float[12][H]
+// ---------------------------------------------------------------------------------
+__global__ void hypothesis_kernel(const uint32_t* __restrict__ draws, const DeviceState* __restrict__ st,
+                                  const float4* __restrict__ pairs, unsigned n_src, int H,
+                                  float* __restrict__ hyp, int* __restrict__ counts) {
+    int h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= H) return;
+    if ((unsigned)(3 * h + 2) >= st->accepted_total) { counts[h] = -3; return; }   // raw window too small
+    uint32_t i0 = draws[3 * h], i1 = draws[3 * h + 1], i2 = draws[3 * h + 2];
+    if (i0 == i1 || i1 == i2 || i0 == i2) {                // registration.cpp:240 `continue`
+        counts[h] = -1;
+#pragma unroll
+        for (int k = 0; k < 12; ++k) hyp[(size_t)k * H + h] = 0.0f;
+        return;
+    }
+    float s[3][3], q[3][3];
+    const uint32_t id[3] = {i0, i1, i2};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        float4 a = pairs[id[k]], b = pairs[n_src + id[k]];
+        s[k][0] = a.x; s[k][1] = a.y; s[k][2] = a.z;
+        q[k][0] = b.x; q[k][1] = b.y; q[k][2] = b.z;
+    }
+    Mat3 R; float t[3];
+    kabsch_three_points(s, q, R, t);
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) hyp[(size_t)(r * 3 + cc) * H + h] = R(r, cc);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) hyp[(size_t)(9 + r) * H + h] = t[r];
+    counts[h] = 0;
+}
+
+__global__ void reset_counts_kernel(int* counts, int h0, int h1) {
+    int h = h0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (h < h1 && counts[h] > 0) counts[h] = 0;
+}
+
+// ---------------------------------------------------------------------------------
+// scoring
+// ---------------------------------------------------------------------------------
+constexpr int kScoreThreads = 256;
+constexpr int kPairTile = 512;        // pairs per smem tile: 2 x 8 KB
+
+template <int KH>
+__global__ void __launch_bounds__(kScoreThreads)
+score_exact_kernel(const float* __restrict__ hyp, int H, int h0, int h1,
+                   const float4* __restrict__ pairs, unsigned n_pairs, unsigned pairs_per_y,
+                   float cut, int* __restrict__ counts) {
+    __shared__ float4 sS[kPairTile];
+    __shared__ float4 sQ[kPairTile];
+    const int tid = threadIdx.x;
+    float R[KH][9], t[KH][3];
+    int cnt[KH], hid[KH];
+#pragma unroll
+    for (int k = 0; k < KH; ++k) {
+        int h = h0 + (blockIdx.x * KH + k) * kScoreThreads + tid;
+        hid[k] = h;
+        int hc = h < h1 ? h : h1 - 1;
+#pragma unroll
+        for (int e = 0; e < 9; ++e) R[k][e] = hyp[(size_t)e * H + hc];
+#pragma unroll
+        for (int e = 0; e < 3; ++e) t[k][e] = hyp[(size_t)(9 + e) * H + hc];
+        cnt[k] = 0;
+    }
+    const unsigned p_begin = blockIdx.y * pairs_per_y;
+    const unsigned p_end = min(n_pairs, p_begin + pairs_per_y);
+    for (unsigned base = p_begin; base < p_end; base += kPairTile) {
+        const unsigned m = min((unsigned)kPairTile, p_end - base);
+        __syncthreads();
+        for (unsigned e = tid; e < m; e += kScoreThreads) { sS[e] = pairs[base + e]; sQ[e] = pairs[n_pairs + base + e]; }
+        __syncthreads();
+#pragma unroll 4
+        for (unsigned j = 0; j < m; ++j) {
+            const float4 s = sS[j], q = sQ[j];
+#pragma unroll
+            for (int k = 0; k < KH; ++k) {
+                // (R s + t - q) in the reference's evaluation order, no contraction
+                float x = (R[k][0] * s.x + (R[k][1] * s.y + R[k][2] * s.z)) + t[k][0];
+                float y = (R[k][3] * s.x + (R[k][4] * s.y + R[k][5] * s.z)) + t[k][1];
+                float z = (R[k][6] * s.x + (R[k][7] * s.y + R[k][8] * s.z)) + t[k][2];
+                float dx = x - q.x, dy = y - q.y, dz = z - q.z;
+                float d2 = dx * dx + (dy * dy + dz * dz);
+                cnt[k] += (d2 < cut) ? 1 : 0;
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < KH; ++k) {
+        int h = hid[k];
+        if (h < h1 && counts[h] >= 0) {
+            if (gridDim.y == 1) counts[h] = cnt[k];
+            else if (cnt[k]) atomicAdd(&counts[h], cnt[k]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// selection
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v) {
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+        unsigned long long o = __shfl_xor_sync(0xffffffffu, v, m);
+        v = o > v ? o : v;
+    }
+    return v;
+}
+
+// mode 0: exit key (first id with fitness > confidence).  mode 1: best key over ids <= limit.
+__global__ void select_kernel(const int* __restrict__ counts, int h0, int h1, float n_src_f, float confidence,
+                              int mode, const long long* __restrict__ limit_key, unsigned long long* __restrict__ out_key) {
+    unsigned limit_id = 0xFFFFFFFFu;
+    if (mode == 1 && limit_key) {
+        unsigned long long lk = (unsigned long long)(*limit_key);
+        if (lk != 0ull) limit_id = 0xFFFFFFFFu - (unsigned)(lk & 0xFFFFFFFFull);
+    }
+    unsigned long long best = 0ull;
+    for (int h = h0 + blockIdx.x * blockDim.x + threadIdx.x; h < h1; h += gridDim.x * blockDim.x) {
+        int c = counts[h];
+        if (c <= 0) continue;
+        float fitness = (float)c / n_src_f;                       // registration.cpp:281
+        unsigned long long key;
+        if (mode == 0) { if (!(fitness > confidence)) continue; key = (unsigned long long)(0xFFFFFFFFu - (unsigned)h); }
+        else {
+            if ((unsigned)h > limit_id) continue;
+            if (!(fitness > 0.0f)) continue;                      // best_result.fitness starts at 0 (registration.hpp:28)
+            key = ((unsigned long long)__float_as_uint(fitness) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)h);
+        }
+        best = key > best ? key : best;
+    }
+    best = warp_max_u64(best);
+    __shared__ unsigned long long wbest[32];
+    if ((threadIdx.x & 31) == 0) wbest[threadIdx.x >> 5] = best;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        unsigned long long v = (threadIdx.x < (blockDim.x >> 5)) ? wbest[threadIdx.x] : 0ull;
+        v = warp_max_u64(v);
+        if (threadIdx.x == 0 && v) atomicMax(out_key, v);
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// winner: transform, fitness, and rmse with the reference's sequential fp32 sum
+// (registration.cpp:270-282).  One block; inlier errors are compacted in order, then
+// a single thread adds them left to right.
+// ---------------------------------------------------------------------------------
+constexpr int kFinishThreads = 1024;
+
+__global__ void __launch_bounds__(kFinishThreads)
+finish_kernel(const long long* __restrict__ key_ptr, const float* __restrict__ hyp, int H,
+              const float4* __restrict__ pairs, unsigned n_pairs,
+              float n_src_f, float thr, DeviceState* __restrict__ st) {
+    __shared__ float vals[kFinishThreads];
+    __shared__ unsigned warp_cnt[kFinishThreads / 32];
+    __shared__ unsigned tile_total;
+    __shared__ float running;
+    __shared__ int inlier_total;
+    const int tid = threadIdx.x;
+    unsigned long long key = (unsigned long long)(*key_ptr);
+    float* out = st->out18;
+    if (key == 0ull) {                                 // no hypothesis ever beat fitness 0
+        if (tid < 16) out[tid] = (tid % 5 == 0) ? 1.0f : 0.0f;
+        if (tid == 16) { out[16] = 0.0f; out[17] = 0.0f; out[18] = __int_as_float(-1); }
+        return;
+    }
+    const int h = (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull));
+    float R[9], t[3];
+#pragma unroll
+    for (int e = 0; e < 9; ++e) R[e] = hyp[(size_t)e * H + h];
+#pragma unroll
+    for (int e = 0; e < 3; ++e) t[e] = hyp[(size_t)(9 + e) * H + h];
+    if (tid == 0) { running = 0.0f; inlier_total = 0; }
+    __syncthreads();
+    for (unsigned base = 0; base < n_pairs; base += kFinishThreads) {
+        unsigned i = base + tid;
+        float e2 = 0.0f; bool in = false;
+        if (i < n_pairs) {
+            float4 s = pairs[i], q = pairs[n_pairs + i];
+            float x = (R[0] * s.x + (R[1] * s.y + R[2] * s.z)) + t[0];
+            float y = (R[3] * s.x + (R[4] * s.y + R[5] * s.z)) + t[1];
+            float z = (R[6] * s.x + (R[7] * s.y + R[8] * s.z)) + t[2];
+            float dx = x - q.x, dy = y - q.y, dz = z - q.z;
+            float err = sqrtf(dx * dx + (dy * dy + dz * dz));
+            in = err < thr;
+            e2 = err * err;
+        }
+        unsigned ballot = __ballot_sync(0xffffffffu, in);
+        unsigned lane = tid & 31, warp = tid >> 5;
+        if (lane == 0) warp_cnt[warp] = __popc(ballot);
+        __syncthreads();
+        if (warp == 0) {
+            unsigned c = warp_cnt[lane];
+            unsigned inc = warp_inclusive_scan(c);
+            warp_cnt[lane] = inc - c;
+            if (lane == 31) tile_total = inc;
+        }
+        __syncthreads();
+        if (in) vals[warp_cnt[warp] + __popc(ballot & ((1u << lane) - 1u))] = e2;
+        __syncthreads();
+        if (tid == 0) {
+            float acc = running; unsigned m = tile_total;
+            for (unsigned k = 0; k < m; ++k) acc += vals[k];
+            running = acc;
+            inlier_total += (int)m;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        int inliers = inlier_total;   // recounted here: the winner may have been scored on another rank
+        float fitness = (float)inliers / n_src_f;
+        float rmse = inliers > 0 ? sqrtf(running / (float)inliers) : 999.0f;
+        // Matrix4f column-major: T(r,c) at c*4 + r
+        for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) out[c * 4 + r] = R[r * 3 + c]; out[12 + r] = t[r]; out[r * 4 + 3] = 0.0f; }
+        out[15] = 1.0f;
+        out[16] = fitness; out[17] = rmse; out[18] = __int_as_float(h);
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------
+static float sqrt_cut(float thr) {
+    // smallest float c with sqrtf(c) >= thr, so that (sqrtf(d2) < thr) <=> (d2 < c) for d2 >= 0
+    if (!(thr > 0.0f)) return 0.0f;                    // err < thr is never true for thr <= 0 (err >= 0)
+    float c = thr * thr;
+    while (sqrtf(c) >= thr && c > 0.0f) c = nextafterf(c, 0.0f);
+    while (sqrtf(c) < thr) c = nextafterf(c, INFINITY);
+    return c;
+}
+
+static int ensure_raw(b3d_ctx* c, size_t need) {
+    if (need <= c->raw_have) return B3D_OK;
+    size_t target = need + need / 16 + 4096;
+    DevBuf grown;
+    B3D_CUDA(c, grown.ensure(sizeof(uint32_t) * target));
+    if (c->raw_have) B3D_CUDA(c, cudaMemcpyAsync(grown.p, c->raw.p, sizeof(uint32_t) * c->raw_have, cudaMemcpyDeviceToDevice, c->stream));
+    size_t add = target - c->raw_have;
+    uint32_t* host = nullptr;
+    B3D_CUDA(c, cudaMallocHost(&host, sizeof(uint32_t) * add));
+    for (size_t i = 0; i < add; ++i) host[i] = (uint32_t)c->host_rng();
+    cudaError_t e = cudaMemcpyAsync(grown.as<uint32_t>() + c->raw_have, host, sizeof(uint32_t) * add, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFreeHost(host);
+    if (e != cudaSuccess) { grown.release(); return fail_cuda(c, e, "raw RNG upload", __FILE__, __LINE__); }
+    c->raw.release();
+    c->raw = grown;
+    c->raw_have = target;
+    return B3D_OK;
+}
+
+int ransac_prepare_impl(b3d_ctx* c, float voxel, int max_iterations, float confidence) {
+    if (!c->have_clouds || !c->have_corr) return fail(c, B3D_ERR_STATE, "ransac_prepare: clouds/correspondences not set");
+    if (max_iterations < 0) return fail(c, B3D_ERR_INVALID, "ransac_prepare: max_iterations < 0");
+    if (c->n_src >= 0xFFFFFFFFull) return fail(c, B3D_ERR_INVALID, "ransac_prepare: n_src must be < 2^32 - 1");
+    c->prepared = false; c->scored = false;
+    c->H = max_iterations;
+    c->ransac_thr = voxel * 1.5f;                       // registration.cpp:213
+    c->ransac_cut = sqrt_cut(c->ransac_thr);
+    c->confidence = confidence;
+    const int H = max_iterations;
+    const unsigned n = (unsigned)c->n_src;
+    if (H == 0 || n == 0) { c->prepared = true; return B3D_OK; }
+    B3D_CUDA(c, c->pairs.ensure(sizeof(float4) * 2 * (size_t)n));
+    B3D_CUDA(c, c->draws.ensure(sizeof(uint32_t) * 3 * (size_t)H));
+    B3D_CUDA(c, c->hyp.ensure(sizeof(float) * 12 * (size_t)H));
+    B3D_CUDA(c, c->counts.ensure(sizeof(int) * (size_t)H));
+
+    const uint32_t range = n;
+    const uint32_t reject_below = (uint32_t)(0u - range) % range;       // 2^32 mod n
+    const double p_rej = (double)reject_below / 4294967296.0;
+    const size_t need = 3 * (size_t)H;
+    size_t window = (size_t)((double)need / (1.0 - p_rej)) + (size_t)(8.0 * sqrt((double)need * p_rej) / (1.0 - p_rej)) + 64;
+
+    for (int attempt = 0; attempt < 4; ++attempt) {
+        int rc = ensure_raw(c, window);
+        if (rc != B3D_OK) return rc;
+        StageTimer timer(c, 1);
+        const unsigned tiles = (unsigned)div_up((long long)window, kScanTile);
+        B3D_CUDA(c, c->scan_tmp.ensure(sizeof(unsigned) * (tiles + 1)));
+        LemireAccept accept{c->raw.as<uint32_t>(), range, reject_below};
+        DrawEmit emit{c->raw.as<uint32_t>(), range, c->draws.as<uint32_t>(), (unsigned)need};
+        DeviceState* st = c->state.as<DeviceState>();
+        scan_tile_sums_kernel<<<tiles, kScanThreads, 0, c->stream>>>(accept, (unsigned)window, c->scan_tmp.as<unsigned>());
+        B3D_LAUNCHED(c);
+        scan_tile_offsets_kernel<<<1, kScanThreads, 0, c->stream>>>(c->scan_tmp.as<unsigned>(), tiles, &st->accepted_total);
+        B3D_LAUNCHED(c);
+        scan_emit_kernel<<<tiles, kScanThreads, 0, c->stream>>>(accept, emit, (unsigned)window, c->scan_tmp.as<unsigned>());
+        B3D_LAUNCHED(c);
+        if (attempt == 0) {
+            gather_pairs_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(c->src4.as<float4>(), c->tgt4.as<float4>(),
+                                                                          c->corr.as<uint32_t>(), n, (unsigned)c->n_tgt, c->pairs.as<float4>());
+            B3D_LAUNCHED(c);
+        }
+        hypothesis_kernel<<<div_up(H, 128), 128, 0, c->stream>>>(c->draws.as<uint32_t>(), st, c->pairs.as<float4>(), n, H,
+                                                                   c->hyp.as<float>(), c->counts.as<int>());
+        B3D_LAUNCHED(c);
+        // The acceptance window is sized 8 sigma above the expectation; verify it on the host only
+        // when rejections are frequent enough for that to matter (huge clouds).
+        if (p_rej < 1e-3) break;
+        B3D_CUDA(c, cudaMemcpyAsync(&c->h_state->accepted_total, &st->accepted_total, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+        B3D_CUDA(c, cudaStreamSynchronize(c->stream));
+        if (c->h_state->accepted_total >= need) break;
+        if (attempt == 3) return fail(c, B3D_ERR_RNG_WINDOW, "ransac_prepare: RNG acceptance window exhausted");
+        window *= 2;
+    }
+    c->prepared = true;
+    return B3D_OK;
+}
+
+int ransac_score_impl(b3d_ctx* c, int h0, int h1) {
+    if (!c->prepared) return fail(c, B3D_ERR_STATE, "ransac_score: call ransac_prepare first");
+    if (h0 < 0 || h1 > c->H || h0 > h1) return fail(c, B3D_ERR_INVALID, "ransac_score: bad hypothesis range");
+    c->scored = true; c->scored_lo = h0; c->scored_hi = h1;
+    if (h0 == h1 || c->n_src == 0) return B3D_OK;
+    StageTimer timer(c, 2);
+    const unsigned n = (unsigned)c->n_src;
+    const int nh = h1 - h0;
+    // KH = 2 hypotheses per thread when there are enough of them to fill the machine twice over
+    const int KH = (nh >= 2 * kNumSMs * kScoreThreads * 4) ? 2 : 1;
+    const int bx = div_up(nh, kScoreThreads * KH);
+    // Split the pair stream so that the grid is many waves deep: blocks are long-running and
+    // compute-bound, so a shallow grid loses up to a full wave to the tail.
+    int by = 1;
+    const int want_blocks = kNumSMs * 64;
+    if (bx < want_blocks) by = min(div_up(want_blocks, bx), div_up((long long)n, kPairTile * 4));
+    if (by < 1) by = 1;
+    unsigned per_y = (unsigned)div_up((long long)n, by);
+    per_y = (unsigned)div_up(per_y, kPairTile) * kPairTile;
+    by = div_up((long long)n, per_y);
+    if (by > 1) {
+        reset_counts_kernel<<<div_up(nh, 256), 256, 0, c->stream>>>(c->counts.as<int>(), h0, h1);
+        B3D_LAUNCHED(c);
+    }
+    dim3 grid(bx, by);
+    if (KH == 2)
+        score_exact_kernel<2><<<grid, kScoreThreads, 0, c->stream>>>(c->hyp.as<float>(), c->H, h0, h1, c->pairs.as<float4>(), n, per_y,
+                                                                     c->ransac_cut, c->counts.as<int>());
+    else
+        score_exact_kernel<1><<<grid, kScoreThreads, 0, c->stream>>>(c->hyp.as<float>(), c->H, h0, h1, c->pairs.as<float4>(), n, per_y,
+                                                                     c->ransac_cut, c->counts.as<int>());
+    B3D_LAUNCHED(c);
+    return B3D_OK;
+}
+
+int ransac_reduce_impl(b3d_ctx* c, int h0, int h1, const int64_t* limit_key_dev, int64_t* keys_dev) {
+    if (!c->prepared) return fail(c, B3D_ERR_STATE, "ransac_reduce: call ransac_prepare first");
+    if (h0 < 0 || h1 > c->H || h0 > h1 || !keys_dev) return fail(c, B3D_ERR_INVALID, "ransac_reduce: bad arguments");
+    StageTimer timer(c, 3);
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(keys_dev);
+    const float n_src_f = (float)c->n_src;              // size_t -> float, as `inliers / source.size()` does
+    const int blocks = grid_for(h1 - h0, 256, 4);
+    if (!limit_key_dev) {
+        B3D_CUDA(c, cudaMemsetAsync(keys, 0, 2 * sizeof(unsigned long long), c->stream));
+        if (h1 > h0 && c->n_src) {
+            select_kernel<<<blocks, 256, 0, c->stream>>>(c->counts.as<int>(), h0, h1, n_src_f, c->confidence, 0, nullptr, keys + 1);
+            B3D_LAUNCHED(c);
+            select_kernel<<<blocks, 256, 0, c->stream>>>(c->counts.as<int>(), h0, h1, n_src_f, c->confidence, 1,
+                                                         reinterpret_cast<const long long*>(keys + 1), keys);
+            B3D_LAUNCHED(c);
+        }
+    } else {
+        B3D_CUDA(c, cudaMemsetAsync(keys, 0, sizeof(unsigned long long), c->stream));
+        if (h1 > h0 && c->n_src) {
+            select_kernel<<<blocks, 256, 0, c->stream>>>(c->counts.as<int>(), h0, h1, n_src_f, c->confidence, 1,
+                                                         reinterpret_cast<const long long*>(limit_key_dev), keys);
+            B3D_LAUNCHED(c);
+        }
+    }
+    return B3D_OK;
+}
+
+int ransac_finish_impl(b3d_ctx* c, const int64_t* keys_dev, float* T, float* fitness, float* rmse, int32_t* best) {
+    if (!c->prepared || !keys_dev) return fail(c, B3D_ERR_STATE, "ransac_finish: not prepared");
+    DeviceState* st = c->state.as<DeviceState>();
+    if (c->H == 0 || c->n_src == 0) {
+        for (int i = 0; i < 16; ++i) T[i] = (i % 5 == 0) ? 1.0f : 0.0f;
+        *fitness = 0.0f; *rmse = 0.0f; if (best) *best = -1;
+        return B3D_OK;
+    }
+    {
+        StageTimer timer(c, 3);
+        finish_kernel<<<1, kFinishThreads, 0, c->stream>>>(reinterpret_cast<const long long*>(keys_dev), c->hyp.as<float>(), c->H,
+                                                           c->pairs.as<float4>(), (unsigned)c->n_src,
+                                                           (float)c->n_src, c->ransac_thr, st);
+        B3D_LAUNCHED(c);
+    }
+    B3D_CUDA(c, cudaMemcpyAsync(c->h_state->out18, st->out18, sizeof(float) * 20, cudaMemcpyDeviceToHost, c->stream));
+    B3D_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < 16; ++i) T[i] = c->h_state->out18[i];
+    *fitness = c->h_state->out18[16];
+    *rmse = c->h_state->out18[17];
+    int32_t id; memcpy(&id, &c->h_state->out18[18], sizeof(id));
+    if (best) *best = id;
+    return B3D_OK;
+}
+
+}  // namespace b3d

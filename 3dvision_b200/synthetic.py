@@ -1,0 +1,135 @@
+"""Deterministic synthetic workloads for the registration hot path (numpy only).
+
+These build the inputs of BASELINE.json's configs.  Seeds are
+``1234 + config id``.  Nothing here touches the GPU or the oracle; tests and
+bench.py feed the same arrays to both.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+
+def _rot(axis, angle_rad):
+    axis = np.asarray(axis, np.float64)
+    axis = axis / np.linalg.norm(axis)
+    K = np.array([[0, -axis[2], axis[1]], [axis[2], 0, -axis[0]], [-axis[1], axis[0], 0]])
+    return np.eye(3) + np.sin(angle_rad) * K + (1 - np.cos(angle_rad)) * (K @ K)
+
+
+def rigid(axis, angle_deg, t) -> np.ndarray:
+    T = np.eye(4)
+    T[:3, :3] = _rot(axis, np.deg2rad(angle_deg))
+    T[:3, 3] = t
+    return T
+
+
+def apply(T, pts):
+    return (pts.astype(np.float64) @ T[:3, :3].T + T[:3, 3]).astype(np.float32)
+
+
+def _bumpy_torus_xyz(u, v, R, r):
+    rho = R * (1.0 + 0.20 * np.cos(2.0 * u) + 0.10 * np.sin(3.0 * u))      # major radius varies with u:
+    rr = r * (1.0 + 0.30 * np.cos(u + 1.0))                                 # not a surface of revolution,
+    x = (rho + rr * np.cos(v)) * np.cos(u)                                  # so the pose is fully observable
+    y = (rho + rr * np.cos(v)) * np.sin(u)
+    z = rr * np.sin(v) + 0.25 * R * np.sin(2.0 * u + 0.3)
+    return np.stack([x, y, z], 1)
+
+
+def torus(n, rng, R=0.08, r=0.03, center=(0.0, 0.0, 0.6)):
+    """n points on an asymmetric ("bumpy") torus, metres, with unit outward normals.
+
+    Normals are the normalised cross product of central-difference tangents in float64
+    (accurate to ~1e-9), oriented away from the tube's centre curve.
+    """
+    u = rng.uniform(0, 2 * np.pi, n)
+    v = rng.uniform(0, 2 * np.pi, n)
+    P = _bumpy_torus_xyz(u, v, R, r)
+    h = 1e-6
+    du = (_bumpy_torus_xyz(u + h, v, R, r) - _bumpy_torus_xyz(u - h, v, R, r)) / (2 * h)
+    dv = (_bumpy_torus_xyz(u, v + h, R, r) - _bumpy_torus_xyz(u, v - h, R, r)) / (2 * h)
+    nrm = np.cross(du, dv)
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    axis_pt = _bumpy_torus_xyz(u, v, R, 0.0)                                # centre curve of the tube
+    flip = np.sum(nrm * (P - axis_pt), axis=1) < 0
+    nrm[flip] *= -1.0
+    return (P + np.asarray(center)).astype(np.float32), nrm.astype(np.float32)
+
+
+def histograms(n, rng, sparsity=0.5):
+    """n x 33 non-negative, L1-normalised descriptors shaped like FPFH rows (registration.cpp:192-194)."""
+    d = rng.gamma(0.6, 1.0, (n, 33))
+    d *= rng.random((n, 33)) > sparsity * rng.random((n, 1))
+    d[:, 0] += 1e-3
+    d /= d.sum(1, keepdims=True)
+    return d.astype(np.float32)
+
+
+@dataclass
+class IcpCase:
+    source: np.ndarray        # (Ns,3) scene points
+    target: np.ndarray        # (Nt,3) model points
+    target_normals: np.ndarray
+    T_init: np.ndarray        # 4x4, coarse source->target
+    T_true: np.ndarray        # 4x4, exact source->target (before noise)
+    threshold: float
+    iterations: int
+
+
+def icp_case(n_model=100_000, n_scene=300_000, seed=1234 + 2, noise=0.0005, threshold=0.005,
+             iterations=50, init_angle_deg=0.5, init_shift=0.0015) -> IcpCase:
+    """configs[1]: model on an analytic surface + normals; scene = resampled model, moved, noisy."""
+    rng = np.random.default_rng(seed)
+    model, normals = torus(n_model, rng)
+    scene_on_model, _ = torus(n_scene, rng)
+    T_model_to_scene = rigid([0.3, -0.5, 0.8], 7.0, [0.012, -0.008, 0.015])
+    scene = apply(T_model_to_scene, scene_on_model)
+    scene = (scene + rng.normal(0, noise, scene.shape)).astype(np.float32)
+    T_true = np.linalg.inv(T_model_to_scene)
+    T_init = rigid([0.7, 0.2, -0.4], init_angle_deg, [init_shift, -init_shift * 0.5, init_shift * 0.3]) @ T_true
+    return IcpCase(scene, model, normals, T_init.astype(np.float32), T_true.astype(np.float32), threshold, iterations)
+
+
+@dataclass
+class RansacCase:
+    source: np.ndarray
+    target: np.ndarray
+    source_desc: np.ndarray
+    target_desc: np.ndarray
+    voxel_size: float
+    max_iterations: int
+    T_true: np.ndarray
+    true_match: np.ndarray    # (Ns,) index into target, -1 for outliers
+
+
+def ransac_case(n_src=100_000, n_tgt=100_000, seed=1234 + 3, inlier_frac=0.7, voxel=0.001,
+                noise=0.0003, desc_noise=0.002, max_iterations=1_000_000) -> RansacCase:
+    """configs[2]: correspondences from descriptor matching, 70 % true matches, 30 % outliers."""
+    rng = np.random.default_rng(seed)
+    target, _ = torus(n_tgt, rng, R=0.25, r=0.09)
+    tdesc = histograms(n_tgt, rng)
+    T_true = rigid([0.2, 0.9, -0.3], 25.0, [0.05, -0.03, 0.08])         # source -> target
+    T_inv = np.linalg.inv(T_true)
+    match = rng.integers(0, n_tgt, n_src)
+    inl = rng.random(n_src) < inlier_frac
+    src = apply(T_inv, target[match]) + rng.normal(0, noise, (n_src, 3)).astype(np.float32)
+    lo, hi = src.min(0), src.max(0)
+    src[~inl] = rng.uniform(lo, hi, ((~inl).sum(), 3)).astype(np.float32)
+    sdesc = np.abs(tdesc[match] + rng.normal(0, desc_noise, (n_src, 33)).astype(np.float32))
+    sdesc /= sdesc.sum(1, keepdims=True)
+    sdesc[~inl] = histograms(int((~inl).sum()), rng)
+    true_match = np.where(inl, match, -1)
+    return RansacCase(src.astype(np.float32), target, sdesc.astype(np.float32), tdesc, voxel, max_iterations,
+                      T_true.astype(np.float32), true_match)
+
+
+def rotation_error(Ta, Tb) -> float:
+    """Frobenius norm of the rotation-block difference (north_star tolerance: 1e-5)."""
+    return float(np.linalg.norm(np.asarray(Ta, np.float64)[:3, :3] - np.asarray(Tb, np.float64)[:3, :3]))
+
+
+def translation_error(Ta, Tb) -> float:
+    """Euclidean norm of the translation difference in metres (north_star tolerance: 1e-6)."""
+    return float(np.linalg.norm(np.asarray(Ta, np.float64)[:3, 3] - np.asarray(Tb, np.float64)[:3, 3]))

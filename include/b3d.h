@@ -1,0 +1,155 @@
+/* =============================================================================
+ * b3d.h — C-ABI of the B200-native registration hot path.
+ *
+ * This is the drop-in boundary for ONE path of stojicnnnn/3DVision: FPFH
+ * descriptor matching + RANSAC + ICP.  Every entry point cites the reference
+ * interface it replaces (paths relative to the reference repo).  Plain pointers
+ * and sizes only; no C++/torch types; functions never throw — they return 0 on
+ * success or a negative b3d_status.  There is NO CPU fallback: without a usable
+ * CUDA device every compute entry point returns B3D_ERR_NO_DEVICE.
+ *
+ * Layout conventions (identical to the reference's in-memory types):
+ *   points / normals : packed float xyz, 12 B per point
+ *                      (std::vector<Eigen::Vector3f>, include/registration.hpp:10-19)
+ *   descriptors      : row-major float[n][33], 132 B stride
+ *                      (std::vector<std::array<float,33>>, include/registration.hpp:21-24)
+ *   transforms       : float[16] column-major (Eigen::Matrix4f storage,
+ *                      include/registration.hpp:26-30)
+ * Threading: a b3d_ctx is single-threaded; use one context per host thread
+ * (the orchestrator calls from a pool, src/pipeline.cpp:321-327).  Contexts are
+ * independent (own stream + workspace) and may run concurrently.
+ * ============================================================================= */
+#ifndef B3D_H_
+#define B3D_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b3d_ctx b3d_ctx;
+
+typedef enum b3d_status {
+    B3D_OK             = 0,
+    B3D_ERR_NO_DEVICE  = -1,   /* no CUDA device / driver: caller's catch(...) path (src/pipeline.cpp:114) */
+    B3D_ERR_CUDA       = -2,   /* a CUDA runtime call or kernel failed; see b3d_last_error() */
+    B3D_ERR_INVALID    = -3,   /* bad argument (null pointer, size 0 where not allowed, ...) */
+    B3D_ERR_ALLOC      = -4,   /* device or host allocation failed */
+    B3D_ERR_STATE      = -5,   /* staged call issued out of order */
+    B3D_ERR_RNG_WINDOW = -6    /* internal: raw RNG window too small (retried automatically) */
+} b3d_status;
+
+#define B3D_DESC_DIM 33
+#define B3D_NO_MATCH 0xFFFFFFFFu
+
+/* ---- lifetime ---------------------------------------------------------------- */
+
+/* GPURegistration::isCudaAvailable(), include/gpu_registration.hpp:18 (src/gpu_impl.cpp).
+ * 1 if a CUDA device with compute capability 10.x is usable, else 0. Never fails. */
+int b3d_cuda_available(void);
+
+/* Creates a context on `device` (stream + persistent workspace; no cudaMalloc on
+ * the steady-state call path).  Replaces the per-call cudaMalloc/cudaFree block of
+ * GPURegistration::icpRefine, src/gpu_impl.cpp:155-186, 246-255. */
+int  b3d_ctx_create(int device, b3d_ctx** out);
+void b3d_ctx_destroy(b3d_ctx* ctx);
+
+/* Run all work of this context on an externally owned cudaStream_t (e.g. the
+ * current torch stream) instead of the context's own stream. NULL restores it. */
+int b3d_ctx_set_stream(b3d_ctx* ctx, void* cuda_stream);
+
+const char* b3d_strerror(int status);
+const char* b3d_last_error(const b3d_ctx* ctx);
+
+/* ---- whole-path entry points (host buffers in, 18 floats out) ------------------- */
+
+/* Registration::ransacRegistration(source, target, source_features, target_features,
+ *   voxel_size, max_iterations = 100000, confidence = 0.999f)
+ * include/registration.hpp:40-48, src/registration.cpp:204-295.
+ * Feature matching (strict-< argmin, lowest index on ties), mt19937(42) hypotheses,
+ * inlier scoring at 1.5*voxel_size, strict-> best, early exit on fitness > confidence.
+ * out_best_iteration (optional): id of the winning hypothesis, -1 if none. */
+int b3d_ransac(b3d_ctx* ctx,
+               const float* src_xyz, size_t n_src,
+               const float* tgt_xyz, size_t n_tgt,
+               const float* src_desc, const float* tgt_desc,
+               float voxel_size, int max_iterations, float confidence,
+               float out_T_colmajor[16], float* out_fitness, float* out_rmse,
+               int32_t* out_best_iteration);
+
+/* Registration::icpRefine(source, target, initial_transform, distance_threshold,
+ *   max_iterations = 200, point_to_plane = true)
+ * include/registration.hpp:50-57, src/registration.cpp:297-414; and
+ * GPURegistration::icpRefine(...), include/gpu_registration.hpp:10-16
+ * (src/gpu_impl.cpp:141-260) which is the same call with point_to_plane = 1.
+ * tgt_normals may be NULL (target.hasNormals() == false => point-to-point).
+ * out_iterations (optional): number of iterations whose update was applied. */
+int b3d_icp(b3d_ctx* ctx,
+            const float* src_xyz, size_t n_src,
+            const float* tgt_xyz, const float* tgt_normals_or_null, size_t n_tgt,
+            const float T0_colmajor[16], float distance_threshold,
+            int max_iterations, int point_to_plane,
+            float out_T_colmajor[16], float* out_fitness, float* out_rmse,
+            int32_t* out_iterations);
+
+/* ---- staged API: resident inputs, hypothesis sharding, parity taps ---------------
+ * Call order: set_clouds -> [set_features -> match_features | set_correspondences]
+ *             -> ransac_prepare -> ransac_score -> ransac_reduce -> ransac_finish
+ *             set_clouds -> icp_run
+ * `on_device` != 0 means the pointer is a device pointer valid on the context's
+ * device and stream. */
+
+int b3d_set_clouds(b3d_ctx* ctx, const float* src_xyz, size_t n_src,
+                   const float* tgt_xyz, const float* tgt_normals_or_null, size_t n_tgt, int on_device);
+int b3d_set_features(b3d_ctx* ctx, const float* src_desc, const float* tgt_desc, int on_device);
+
+/* src/registration.cpp:216-232 for source rows [row0,row1). */
+int b3d_match_features(b3d_ctx* ctx, size_t row0, size_t row1);
+int b3d_get_correspondences(b3d_ctx* ctx, uint32_t* out_host /* [n_src] */);
+int b3d_set_correspondences(b3d_ctx* ctx, const uint32_t* corr /* [n_src] */, int on_device);
+/* Device pointer to correspondences[n_src] (uint32), for an all-gather between ranks. */
+int b3d_correspondences_devptr(b3d_ctx* ctx, void** out_devptr);
+
+/* src/registration.cpp:213, 235-268: threshold, RNG stream -> index triples,
+ * 3-point Kabsch (R,t) for hypotheses [0,max_iterations). */
+int b3d_ransac_prepare(b3d_ctx* ctx, float voxel_size, int max_iterations, float confidence);
+/* src/registration.cpp:270-279 for hypothesis ids [h0,h1) (this rank's shard). */
+int b3d_ransac_score(b3d_ctx* ctx, int h0, int h1);
+/* src/registration.cpp:281-290 over ids [h0,h1): writes two int64 keys to keys_dev
+ *   keys[0] = (fitness_bits << 32) | (0xFFFFFFFF - id)   of the local best (0 if none)
+ *   keys[1] = 0xFFFFFFFF - (first id with fitness > confidence)   (0 if none)
+ * Both combine across ranks with MAX.  If limit_key_dev != NULL it points to a
+ * reduced keys[1]; only ids <= that first-exit id are considered for keys[0]. */
+int b3d_ransac_reduce(b3d_ctx* ctx, int h0, int h1, const int64_t* limit_key_dev, int64_t* keys_dev);
+/* Recomputes the winner's transform/fitness/rmse from the globally reduced keys[0]. */
+int b3d_ransac_finish(b3d_ctx* ctx, const int64_t* keys_dev,
+                      float out_T_colmajor[16], float* out_fitness, float* out_rmse, int32_t* out_best_iteration);
+/* Parity taps: per-hypothesis inlier counts (-1 degenerate triple, -2 not scored /
+ * after early exit) and (R row-major 9, t 3) per hypothesis. */
+int b3d_ransac_counts(b3d_ctx* ctx, int h0, int h1, int32_t* out_host);
+int b3d_ransac_hypotheses(b3d_ctx* ctx, int h0, int h1, float* out_host /* 12 per hypothesis */);
+
+/* ICP on resident clouds. stop_on_convergence = 0 disables the |d rmse| < 1e-6 break
+ * (src/registration.cpp:406) for fixed-iteration throughput runs. */
+int b3d_icp_run(b3d_ctx* ctx, const float T0_colmajor[16], float distance_threshold,
+                int max_iterations, int point_to_plane, int stop_on_convergence,
+                float out_T_colmajor[16], float* out_fitness, float* out_rmse, int32_t* out_iterations);
+/* Parity tap for src/registration.cpp:325-338: nearest target of every transformed
+ * source point under T within distance_threshold.  idx = B3D_NO_MATCH where none. */
+int b3d_icp_nearest(b3d_ctx* ctx, const float T_colmajor[16], float distance_threshold,
+                    uint32_t* out_idx_host, float* out_d2_host);
+
+/* ---- instrumentation ---------------------------------------------------------------- */
+/* Number of kernels this context has launched since creation (bench.py: gpu_launches). */
+uint64_t b3d_kernel_launches(const b3d_ctx* ctx);
+/* Device time in ms of the last call of each stage, measured with CUDA events on the
+ * context's stream: 0 match, 1 ransac_prepare, 2 ransac_score, 3 ransac_reduce+finish,
+ * 4 icp grid build, 5 icp iterations. Returns -1 for an unknown stage. */
+float b3d_stage_ms(const b3d_ctx* ctx, int stage);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B3D_H_ */

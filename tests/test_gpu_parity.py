@@ -1,0 +1,262 @@
+"""Parity of the CUDA path (through the C-ABI) against the CPU oracle on seeded inputs.
+
+Bars (north_star): bit-exact correspondence indices, inlier counts and NN indices;
+final transforms within 1e-5 (rotation, Frobenius) and 1e-6 m (translation).
+Caveat carried by every parity claim: the oracle restates Eigen 3.4 arithmetic and is
+itself "parity unpinned" (oracle/registration_oracle.cpp header).
+"""
+import importlib
+
+import numpy as np
+import pytest
+
+syn = importlib.import_module("3dvision_b200.synthetic")
+
+pytestmark = pytest.mark.gpu
+
+ROT_TOL = 1e-5      # Frobenius norm of the rotation-block difference
+TRANS_TOL = 1e-6    # metres
+# Point-to-point mode only.  The reference accumulates the centroids and the cross-covariance
+# sequentially in fp32 (registration.cpp:374-386); over a few thousand points that sum carries
+# ~1e-6 m of rounding noise per iteration *in the reference itself*, and point-to-point ICP
+# converges slowly along the surface, so the noise is amplified to ~1e-4 by the time the
+# |d rmse| < 1e-6 stop fires.  The CUDA path accumulates in fp64 (deterministic, closer to the
+# exact sums), so it cannot land inside the reference's own noise; DESIGN.md "ICP parity".
+P2P_ROT_TOL = 5e-4
+P2P_TRANS_TOL = 2e-4
+
+
+def small_ransac_case(n_src=3000, n_tgt=2500, H=4000, seed=7, **kw):
+    return syn.ransac_case(n_src=n_src, n_tgt=n_tgt, seed=seed, max_iterations=H, **kw)
+
+
+# ------------------------------------------------------------------ feature matching
+@pytest.mark.parametrize("n_src,n_tgt", [(1, 1), (5, 3), (64, 64), (65, 63), (700, 1000), (3000, 2500)])
+def test_match_indices_bit_exact(ctx, oracle, n_src, n_tgt):
+    rng = np.random.default_rng(n_src * 1000 + n_tgt)
+    sd = syn.histograms(n_src, rng); td = syn.histograms(n_tgt, rng)
+    pts_s = rng.random((n_src, 3), dtype=np.float32); pts_t = rng.random((n_tgt, 3), dtype=np.float32)
+    ctx.set_clouds(pts_s, pts_t)
+    ctx.set_features(sd, td)
+    ctx.match_features()
+    got = ctx.get_correspondences()
+    want = oracle.match_features(sd, td)
+    assert np.array_equal(got, want)
+
+
+def test_match_ties_pick_lowest_index(ctx, oracle):
+    """Planar scenes give bit-identical descriptors: the lowest target index must win."""
+    rng = np.random.default_rng(3)
+    base = syn.histograms(7, rng)
+    td = base[rng.integers(0, 7, 500)]              # many exact duplicates
+    sd = base[rng.integers(0, 7, 300)]
+    pts = rng.random((500, 3), dtype=np.float32)
+    ctx.set_clouds(pts[:300], pts)
+    ctx.set_features(sd, td)
+    ctx.match_features()
+    got = ctx.get_correspondences()
+    want = oracle.match_features(sd, td)
+    assert np.array_equal(got, want)
+    for i in range(300):                            # independent check of the tie rule
+        same = np.flatnonzero((td == sd[i]).all(1))
+        assert got[i] == same[0]
+
+
+def test_match_row_range(ctx, oracle):
+    rng = np.random.default_rng(11)
+    sd = syn.histograms(500, rng); td = syn.histograms(400, rng)
+    pts = rng.random((500, 3), dtype=np.float32)
+    ctx.set_clouds(pts, pts[:400]); ctx.set_features(sd, td)
+    ctx.match_features(0, 500)
+    full = ctx.get_correspondences().copy()
+    ctx.set_correspondences(np.zeros(500, np.uint32))
+    ctx.match_features(130, 387)
+    part = ctx.get_correspondences()
+    assert np.array_equal(part[130:387], full[130:387])
+    assert not part[:130].any() and not part[387:].any()
+
+
+# ------------------------------------------------------------------ RANSAC
+def test_rng_triples_and_hypotheses_match_oracle(ctx, oracle):
+    case = small_ransac_case()
+    corr = oracle.match_features(case.source_desc, case.target_desc)
+    ctx.set_clouds(case.source, case.target)
+    ctx.set_correspondences(corr)
+    ctx.ransac_prepare(case.voxel_size, case.max_iterations, 2.0)
+    hyp = ctx.ransac_hypotheses()
+    for it in list(range(0, 40)) + [999, 2500, case.max_iterations - 1]:
+        ok, R, t, _ = oracle.ransac_hypothesis(case.source, case.target, corr, it)
+        if ok:
+            assert np.array_equal(hyp[it, :9].reshape(3, 3), R), f"R differs at hypothesis {it}"
+            assert np.array_equal(hyp[it, 9:], t), f"t differs at hypothesis {it}"
+
+
+@pytest.mark.parametrize("n_src,H", [(3000, 4000), (257, 1500), (40, 600)])
+def test_inlier_counts_bit_exact(ctx, oracle, n_src, H):
+    """Per-hypothesis inlier counts == oracle for every hypothesis, degenerate triples included
+    (small n_src makes i0==i1 collisions and Lemire rejections likely)."""
+    case = small_ransac_case(n_src=n_src, n_tgt=2500, H=H, seed=n_src)
+    corr = oracle.match_features(case.source_desc, case.target_desc)
+    ctx.set_clouds(case.source, case.target)
+    ctx.set_correspondences(corr)
+    ctx.ransac_prepare(case.voxel_size, H, 2.0)
+    ctx.ransac_score()
+    got = ctx.ransac_counts()
+    ref = oracle.ransac(case.source, case.target, corr, case.voxel_size, H, 2.0, want_counts=True)
+    want = ref.extra["counts"]
+    assert np.array_equal(got, want)
+    assert (want == -1).sum() == (got == -1).sum()
+
+
+def test_ransac_end_to_end_matches_oracle(ctx, oracle):
+    case = small_ransac_case(n_src=3000, n_tgt=2500, H=4000)
+    T, fit, rmse, best = ctx.ransac(case.source, case.target, case.source_desc, case.target_desc,
+                                    case.voxel_size, case.max_iterations, 0.999)
+    ref = oracle.ransac_registration(case.source, case.target, case.source_desc, case.target_desc,
+                                     case.voxel_size, case.max_iterations, 0.999)
+    corr = oracle.match_features(case.source_desc, case.target_desc)
+    ref2 = oracle.ransac(case.source, case.target, corr, case.voxel_size, case.max_iterations, 0.999)
+    assert best == ref2.extra["best_iter"]
+    assert np.array_equal(T, ref.transformation)          # same hypothesis, same arithmetic => same bits
+    assert fit == ref.fitness
+    assert rmse == ref.rmse                               # sequential fp32 sum reproduced on device
+    assert syn.rotation_error(T, case.T_true) < 0.05      # and it is the right pose
+
+
+def test_ransac_early_exit_and_first_wins(ctx, oracle):
+    """Noise-free rigid motion: the first non-degenerate triple already has fitness 1.0 > confidence,
+    so the reference breaks there (registration.cpp:290); later, equally good hypotheses must not win."""
+    rng = np.random.default_rng(5)
+    tgt = rng.uniform(-0.2, 0.2, (800, 3)).astype(np.float32)
+    T = syn.rigid([0.1, 0.7, 0.3], 33.0, [0.05, 0.02, -0.04])
+    src = syn.apply(np.linalg.inv(T), tgt)
+    corr = np.arange(800, dtype=np.uint32)
+    ctx.set_clouds(src, tgt); ctx.set_correspondences(corr)
+    ctx.ransac_prepare(0.001, 500, 0.9)
+    ctx.ransac_score()
+    import torch
+    keys = torch.zeros(2, dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    ctx.ransac_reduce(0, 500, keys.data_ptr())
+    Tg, fit, rmse, best = ctx.ransac_finish(keys.data_ptr())
+    ref = oracle.ransac(src, tgt, corr, 0.001, 500, 0.9, want_counts=True)
+    assert best == ref.extra["best_iter"]
+    assert ref.extra["iters_run"] == best + 1             # the oracle stopped right there
+    assert np.array_equal(Tg, ref.transformation) and fit == ref.fitness and rmse == ref.rmse
+
+
+def test_ransac_no_inliers_returns_identity(ctx, oracle):
+    rng = np.random.default_rng(9)
+    src = rng.uniform(-1, 1, (200, 3)).astype(np.float32)
+    tgt = rng.uniform(50, 60, (200, 3)).astype(np.float32)
+    sd = syn.histograms(200, rng); td = syn.histograms(200, rng)
+    T, fit, rmse, best = ctx.ransac(src, tgt, sd, td, 1e-6, 300, 0.999)
+    ref = oracle.ransac_registration(src, tgt, sd, td, 1e-6, 300, 0.999)
+    assert np.array_equal(T, ref.transformation) and fit == ref.fitness and rmse == ref.rmse
+    if ref.fitness == 0.0:
+        assert best == -1 and np.array_equal(T, np.eye(4, dtype=np.float32))
+
+
+def test_ransac_degenerate_inputs(ctx):
+    """max_iterations = 0 and single-point clouds never throw (registration.hpp:27-29 defaults)."""
+    rng = np.random.default_rng(1)
+    sd = syn.histograms(4, rng)
+    pts = rng.random((4, 3), dtype=np.float32)
+    T, fit, rmse, best = ctx.ransac(pts, pts, sd, sd, 0.001, 0, 0.999)
+    assert np.array_equal(T, np.eye(4, dtype=np.float32)) and fit == 0.0 and rmse == 0.0 and best == -1
+    T, fit, rmse, best = ctx.ransac(pts[:1], pts[:1], sd[:1], sd[:1], 0.001, 50, 0.999)
+    assert fit == 0.0 and best == -1                     # every triple is degenerate with one point
+
+
+# ------------------------------------------------------------------ ICP
+def icp_small(seed=21, n_model=6000, n_scene=9000, **kw):
+    return syn.icp_case(n_model=n_model, n_scene=n_scene, seed=seed, **kw)
+
+
+def test_icp_nearest_bit_exact(ctx, oracle):
+    """Iteration-0 NN: same index and same d2 bits wherever the reference keeps the match."""
+    case = icp_small()
+    ref = oracle.icp(case.source, case.target, case.target_normals, case.T_init, case.threshold, 1, True, want_nn0=True)
+    ctx.set_clouds(case.source, case.target, case.target_normals)
+    idx, d2 = ctx.icp_nearest(case.T_init, case.threshold)
+    ref_idx, ref_d2 = ref.extra["nn_idx0"], ref.extra["nn_d2_0"]
+    kept = np.sqrt(ref_d2) <= np.float32(case.threshold)
+    assert kept.sum() > 1000
+    assert np.array_equal(idx[kept], ref_idx[kept])
+    assert np.array_equal(d2[kept], ref_d2[kept])
+    assert (idx[~kept] == 0xFFFFFFFF).all()
+    assert int(kept.sum()) == ref.extra["ncorr"][0]
+
+
+def test_icp_nearest_ties_resolve_to_lowest_index(ctx, oracle):
+    rng = np.random.default_rng(2)
+    base = rng.uniform(-0.05, 0.05, (300, 3)).astype(np.float32)
+    tgt = np.concatenate([base, base, base])[rng.permutation(900)]       # every point three times
+    src = (base + rng.normal(0, 1e-4, base.shape)).astype(np.float32)
+    ctx.set_clouds(src, tgt)
+    idx, d2 = ctx.icp_nearest(np.eye(4, dtype=np.float32), 0.01)
+    ref = oracle.icp(src, tgt, None, np.eye(4, dtype=np.float32), 0.01, 1, False, want_nn0=True)
+    assert np.array_equal(idx, ref.extra["nn_idx0"])
+    assert np.array_equal(d2, ref.extra["nn_d2_0"])
+
+
+@pytest.mark.parametrize("plane", [True, False])
+def test_icp_transform_within_tolerance(ctx, oracle, plane):
+    case = icp_small()
+    ref = oracle.icp(case.source, case.target, case.target_normals, case.T_init, case.threshold, 30, plane)
+    T, fit, rmse, iters = ctx.icp(case.source, case.target, case.target_normals, case.T_init, case.threshold, 30, plane)
+    assert iters == ref.extra["iters_run"]
+    if plane:
+        assert fit == ref.fitness                           # same inlier set at the last iteration
+        assert abs(rmse - ref.rmse) < 1e-7
+    else:
+        assert abs(fit - ref.fitness) < 2e-3 and abs(rmse - ref.rmse) < 1e-6
+    assert syn.rotation_error(T, ref.transformation) < (ROT_TOL if plane else P2P_ROT_TOL)
+    assert syn.translation_error(T, ref.transformation) < (TRANS_TOL if plane else P2P_TRANS_TOL)
+    assert syn.rotation_error(T, case.T_true) < 1e-2        # and it converged to the real pose (sparse model)
+
+
+def test_icp_without_normals_falls_back_to_point_to_point(ctx, oracle):
+    case = icp_small(seed=33, n_model=3000, n_scene=4000)
+    ref = oracle.icp(case.source, case.target, None, case.T_init, case.threshold, 10, True)
+    T, fit, rmse, iters = ctx.icp(case.source, case.target, None, case.T_init, case.threshold, 10, True)
+    assert iters == ref.extra["iters_run"] and abs(fit - ref.fitness) < 2e-3
+    assert syn.rotation_error(T, ref.transformation) < P2P_ROT_TOL
+    assert syn.translation_error(T, ref.transformation) < P2P_TRANS_TOL
+
+
+def test_icp_too_few_correspondences_keeps_initial(ctx, oracle):
+    """n_corr < 3 at iteration 0 => break; result = {initial_transform, 0, 0} (registration.cpp:309-311, 361)."""
+    rng = np.random.default_rng(4)
+    src = rng.uniform(-1, 1, (500, 3)).astype(np.float32)
+    tgt = rng.uniform(10, 11, (400, 3)).astype(np.float32)
+    T0 = syn.rigid([0, 0, 1], 10.0, [0.1, 0.2, 0.3]).astype(np.float32)
+    T, fit, rmse, iters = ctx.icp(src, tgt, None, T0, 0.01, 20, True)
+    assert np.array_equal(T, T0) and fit == 0.0 and rmse == 0.0 and iters == 0
+
+
+def test_icp_identical_clouds_converges_at_iteration_one(ctx, oracle):
+    rng = np.random.default_rng(6)
+    pts, nrm = syn.torus(4000, rng)
+    ref = oracle.icp(pts, pts, nrm, np.eye(4, dtype=np.float32), 0.002, 50, True)
+    T, fit, rmse, iters = ctx.icp(pts, pts, nrm, np.eye(4, dtype=np.float32), 0.002, 50, True)
+    assert ref.extra["iters_run"] == 2 and iters == 2      # converged flag needs iter > 0
+    assert fit == 1.0 and rmse == 0.0
+    assert syn.rotation_error(T, np.eye(4)) < 1e-6 and syn.translation_error(T, np.eye(4)) < 1e-7
+
+
+# ------------------------------------------------------------------ reference-facing interface
+def test_registration_interface_mirrors_reference(b3d, oracle):
+    case = small_ransac_case(n_src=1500, n_tgt=1200, H=1500)
+    src = b3d.PointCloud(points=case.source); tgt = b3d.PointCloud(points=case.target)
+    res = b3d.Registration.ransacRegistration(src, tgt, b3d.FPFHFeatures(case.source_desc), b3d.FPFHFeatures(case.target_desc),
+                                              case.voxel_size, case.max_iterations)
+    ref = oracle.ransac_registration(case.source, case.target, case.source_desc, case.target_desc, case.voxel_size,
+                                     case.max_iterations, 0.999)
+    assert np.array_equal(res.transformation, ref.transformation) and res.fitness == ref.fitness
+    assert b3d.GPURegistration.isCudaAvailable()
+    ic = icp_small(seed=44, n_model=2000, n_scene=2500)
+    tgt = b3d.PointCloud(points=ic.target, normals=ic.target_normals)
+    r1 = b3d.GPURegistration.icpRefine(b3d.PointCloud(points=ic.source), tgt, ic.T_init, ic.threshold, 15)
+    r2 = b3d.Registration.icpRefine(b3d.PointCloud(points=ic.source), tgt, ic.T_init, ic.threshold, 15, True)
+    assert np.array_equal(r1.transformation, r2.transformation)
