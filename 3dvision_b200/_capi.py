@@ -30,7 +30,7 @@ SYMBOLS = [
     "b3d_set_clouds", "b3d_set_features", "b3d_match_features", "b3d_get_correspondences", "b3d_set_correspondences",
     "b3d_correspondences_devptr", "b3d_ransac_prepare", "b3d_ransac_score", "b3d_ransac_reduce", "b3d_ransac_finish",
     "b3d_ransac_counts", "b3d_ransac_hypotheses", "b3d_icp_run", "b3d_icp_nearest",
-    "b3d_kernel_launches", "b3d_stage_ms",
+    "b3d_kernel_launches", "b3d_stage_ms", "b3d_measure_fp32_rate",
 ]
 
 
@@ -93,6 +93,7 @@ def _declare(L):
     L.b3d_kernel_launches.restype = C.c_uint64
     L.b3d_stage_ms.argtypes = [_vp, C.c_int]
     L.b3d_stage_ms.restype = C.c_float
+    L.b3d_measure_fp32_rate.argtypes = [_vp, C.POINTER(C.c_double)]
 
 
 def cuda_available() -> bool:
@@ -159,6 +160,12 @@ class Context:
 
     def stage_ms(self, stage: int) -> float:
         return float(self._L.b3d_stage_ms(self._h, stage))
+
+    def measure_fp32_rate(self) -> float:
+        """Sustained un-fused FMUL+FADD lane-ops/s on this device (scoring-kernel roofline)."""
+        v = C.c_double()
+        self._check(self._L.b3d_measure_fp32_rate(self._h, C.byref(v)))
+        return v.value
 
     # ---- whole path ----
     def ransac(self, src, tgt, src_desc, tgt_desc, voxel_size, max_iterations=100000, confidence=0.999):

@@ -19,6 +19,22 @@ int xyz_to_float4(b3d_ctx* c, const float* xyz_dev, size_t n, float4* out) {
     return B3D_OK;
 }
 
+// Roofline denominator for the scoring kernel: sustained rate of *separate* FMUL and FADD
+// instructions (the reference arithmetic is un-fused), 8 independent chains per thread.
+__global__ void __launch_bounds__(256) fp32_issue_rate_kernel(float* out, float a, float b, int iters) {
+    float x[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = (float)(threadIdx.x + k) * 1e-3f;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { x[k] = x[k] * a; x[k] = x[k] + b; }
+    }
+    float s = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += x[k];
+    if (s == 123.456f) out[0] = s;          // keeps the chains alive; practically never true
+}
+
 static int upload_cloud(b3d_ctx* c, const float* xyz, size_t n, int on_device, DevBuf& stage, DevBuf& dst) {
     B3D_CUDA(c, dst.ensure(sizeof(float4) * (n ? n : 1)));
     if (n == 0) return B3D_OK;
@@ -116,6 +132,29 @@ float b3d_stage_ms(const b3d_ctx* c, int stage) {
     if (cudaEventSynchronize(c->ev_stop[stage]) != cudaSuccess) { cudaGetLastError(); return -1.0f; }
     if (cudaEventElapsedTime(&ms, c->ev_start[stage], c->ev_stop[stage]) != cudaSuccess) { cudaGetLastError(); return -1.0f; }
     return ms;
+}
+
+int b3d_measure_fp32_rate(b3d_ctx* c, double* out_ops_per_second) {
+    if (!c || !out_ops_per_second) return B3D_ERR_INVALID;
+    B3D_CUDA(c, cudaSetDevice(c->device));
+    B3D_CUDA(c, c->seqsum.ensure(64));
+    const int iters = 1 << 14, blocks = kNumSMs * 8, threads = 256;
+    cudaEvent_t e0, e1;
+    B3D_CUDA(c, cudaEventCreate(&e0)); B3D_CUDA(c, cudaEventCreate(&e1));
+    float best_ms = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(e0, c->stream);
+        fp32_issue_rate_kernel<<<blocks, threads, 0, c->stream>>>(c->seqsum.as<float>(), 0.999999f, 1e-7f, iters);
+        c->launches++;
+        cudaEventRecord(e1, c->stream);
+        cudaError_t e = cudaEventSynchronize(e1);
+        if (e != cudaSuccess) { cudaEventDestroy(e0); cudaEventDestroy(e1); return fail_cuda(c, e, "fp32 rate kernel", __FILE__, __LINE__); }
+        float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best_ms) best_ms = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *out_ops_per_second = (double)blocks * threads * (double)iters * 16.0 / ((double)best_ms * 1e-3);
+    return B3D_OK;
 }
 
 // ---- staged API -------------------------------------------------------------------------

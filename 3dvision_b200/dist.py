@@ -1,0 +1,105 @@
+"""Hypothesis / row sharding of ransacRegistration over torch.distributed (one process per GPU).
+
+The reference has no multi-GPU code; this is the §8(e) design:
+  * descriptor matching: source rows split across ranks, index slices combined with one
+    all-reduce (each rank contributes zeros outside its slice);
+  * hypotheses: rank g scores ids [g*H/G, (g+1)*H/G) against the replicated pair array;
+  * selection: two 8-byte MAX all-reduces reproduce the sequential rule of
+    registration.cpp:284-290 exactly —
+      keys[1] = 0xFFFFFFFF - (first id with fitness > confidence)   (early exit)
+      keys[0] = (fitness_bits << 32) | (0xFFFFFFFF - id), restricted to ids <= that exit id
+    so the winner is (max fitness, min id) among the iterations the reference would have run;
+  * the winner's transform / fitness / rmse are recomputed on every rank from its id.
+Single-cloud ICP does not shard ("replicas only").
+
+The protocol is written against a small backend interface so the same code runs over NCCL
+with the CUDA context and over gloo with a CPU stand-in in the tests.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def shard_range(total: int, rank: int, world: int):
+    """Contiguous, balanced [lo, hi) of `total` items for `rank` of `world`."""
+    return (total * rank) // world, (total * (rank + 1)) // world
+
+
+def pack_best_key(fitness: float, hyp_id: int) -> int:
+    """(fitness_bits << 32) | (0xFFFFFFFF - id): MAX picks the highest fitness, then the lowest id."""
+    bits = int(np.float32(fitness).view(np.uint32))
+    return (bits << 32) | (0xFFFFFFFF - int(hyp_id))
+
+
+def unpack_best_key(key: int):
+    if key == 0:
+        return 0.0, -1
+    fitness = float(np.uint32(key >> 32).view(np.float32))
+    return fitness, 0xFFFFFFFF - (key & 0xFFFFFFFF)
+
+
+def pack_exit_key(hyp_id: int) -> int:
+    return 0xFFFFFFFF - int(hyp_id)
+
+
+class _DevArray:
+    def __init__(self, ptr: int, n: int, typestr: str):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+class CudaBackend:
+    """Adapter from a b3d Context (clouds + features already resident) to the protocol."""
+
+    def __init__(self, ctx, n_src: int):
+        self.ctx = ctx
+        self.n_src = n_src
+        self.keys = torch.zeros(2, dtype=torch.int64, device="cuda")
+        ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+        self._corr = torch.as_tensor(_DevArray(ctx.correspondences_devptr(), max(n_src, 1), "<i4"), device="cuda")
+
+    def match_rows(self, r0, r1):
+        self._corr.zero_()
+        self.ctx.match_features(r0, r1)
+        return self._corr
+
+    def correspondences_ready(self):
+        self.ctx.mark_correspondences_set()
+
+    def prepare(self, voxel, H, confidence):
+        self.ctx.ransac_prepare(voxel, H, confidence)
+
+    def score(self, h0, h1):
+        self.ctx.ransac_score(h0, h1)
+
+    def reduce(self, h0, h1, with_limit):
+        k = self.keys
+        self.ctx.ransac_reduce(h0, h1, k.data_ptr(), k[1:].data_ptr() if with_limit else None)
+        return k
+
+    def finish(self):
+        return self.ctx.ransac_finish(self.keys.data_ptr())
+
+
+def sharded_ransac(backend, voxel_size: float, max_iterations: int, confidence: float, group=None,
+                   match: bool = True):
+    """Run ransacRegistration with rows and hypotheses sharded over `group`. Returns
+    (T 4x4, fitness, rmse, best_iteration) — identical on every rank."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if match:
+        r0, r1 = shard_range(backend.n_src, rank, world)
+        corr = backend.match_rows(r0, r1)
+        if world > 1:
+            dist.all_reduce(corr, op=dist.ReduceOp.SUM, group=group)     # disjoint slices, zeros elsewhere
+        backend.correspondences_ready()
+    backend.prepare(voxel_size, max_iterations, confidence)
+    h0, h1 = shard_range(max_iterations, rank, world)
+    backend.score(h0, h1)
+    keys = backend.reduce(h0, h1, with_limit=False)
+    if world > 1:
+        dist.all_reduce(keys[1:2], op=dist.ReduceOp.MAX, group=group)    # global first-exit id
+        keys = backend.reduce(h0, h1, with_limit=True)                   # best among ids <= exit id
+        dist.all_reduce(keys[0:1], op=dist.ReduceOp.MAX, group=group)
+    return backend.finish()

@@ -102,13 +102,14 @@ class RansacCase:
     max_iterations: int
     T_true: np.ndarray
     true_match: np.ndarray    # (Ns,) index into target, -1 for outliers
+    target_normals: np.ndarray = None
 
 
 def ransac_case(n_src=100_000, n_tgt=100_000, seed=1234 + 3, inlier_frac=0.7, voxel=0.001,
                 noise=0.0003, desc_noise=0.002, max_iterations=1_000_000) -> RansacCase:
     """configs[2]: correspondences from descriptor matching, 70 % true matches, 30 % outliers."""
     rng = np.random.default_rng(seed)
-    target, _ = torus(n_tgt, rng, R=0.25, r=0.09)
+    target, tnormals = torus(n_tgt, rng, R=0.25, r=0.09)
     tdesc = histograms(n_tgt, rng)
     T_true = rigid([0.2, 0.9, -0.3], 25.0, [0.05, -0.03, 0.08])         # source -> target
     T_inv = np.linalg.inv(T_true)
@@ -122,7 +123,7 @@ def ransac_case(n_src=100_000, n_tgt=100_000, seed=1234 + 3, inlier_frac=0.7, vo
     sdesc[~inl] = histograms(int((~inl).sum()), rng)
     true_match = np.where(inl, match, -1)
     return RansacCase(src.astype(np.float32), target, sdesc.astype(np.float32), tdesc, voxel, max_iterations,
-                      T_true.astype(np.float32), true_match)
+                      T_true.astype(np.float32), true_match, tnormals)
 
 
 def rotation_error(Ta, Tb) -> float:

@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""bench.py — registration hot-path benchmark (contract in the task statement, section 4).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Headline: RANSAC hypotheses/s of one whole Registration::ransacRegistration call
+(FPFH matching + hypothesis generation + inlier scoring + selection) on BASELINE.json
+configs[2]: Ns = Nt = 100 000 descriptors / correspondences, H = 1 000 000 hypotheses.
+N > 1 shards source rows and hypothesis ids across ranks (strong scaling, two 8-byte
+all-reduces).  `value` is device time with inputs resident in HBM; `e2e` goes through the
+reference-facing C-ABI call with pinned HOST buffers (H2D + D2H inside the timed region).
+`also` carries the other two figures BASELINE.json's metric names: ICP iterations/s on
+configs[1] (300k x 100k point-to-plane, 50 iterations) and full registration ms.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+OPS_PER_PAIR = 28          # un-fused fp32 ops per (hypothesis, correspondence)
+N_SRC = N_TGT = 100_000
+N_HYP = 1_000_000
+WORKLOAD = "configs[2]: FPFH match + RANSAC, Ns=Nt=100k descriptors/correspondences, H=1M hypotheses"
+
+
+# ----------------------------------------------------------------------------- helpers
+class ClockSampler:
+    """nvidia-smi clock / throttle sampling during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=self.tmp, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self) -> dict:
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.tmp.flush(); self.tmp.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.tmp.read().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        self.tmp.close()
+        try:
+            os.unlink(self.tmp.name)
+        except OSError:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def pinned(a: np.ndarray):
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    return t, t.numpy()
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+# ----------------------------------------------------------------------------- CPU baseline (oracle)
+def cpu_sample(case, corr_cache: dict, threads: int, match_rows: int, hyps: int):
+    """Time the oracle on a bounded slice of the workload; every figure is exactly linear in the
+    sliced dimension. Returns per-thread seconds for (match slice, ransac slice)."""
+    from oracle import oracle as O
+    if "corr" not in corr_cache:
+        corr_cache["corr"] = np.where(case.true_match >= 0, case.true_match, 0).astype(np.uint32)
+    corr = corr_cache["corr"]
+    times = [None] * threads
+
+    def work(i):
+        t0 = time.perf_counter()
+        O.match_features(case.source_desc, case.target_desc, 0, match_rows)
+        t1 = time.perf_counter()
+        O.ransac(case.source, case.target, corr, case.voxel_size, hyps, 2.0)
+        t2 = time.perf_counter()
+        times[i] = (t1 - t0, t2 - t1)
+
+    ths = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    return max(t[0] for t in times), max(t[1] for t in times)
+
+
+def cpu_rate(case, threads, match_rows, hyps, cache):
+    tm, tr = cpu_sample(case, cache, threads, match_rows, hyps)
+    full_s = tm * (N_SRC / match_rows) + tr * (N_HYP / hyps)        # one full ransacRegistration on one core
+    return threads * N_HYP / full_s, tm, tr, full_s
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port; the real registration.cpp needs
+    Eigen and cannot be compiled here) on the host cores, on a bounded sample per step."""
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    O.lib()
+    syn = importlib.import_module("3dvision_b200.synthetic")
+    case = syn.ransac_case(n_src=N_SRC, n_tgt=N_TGT, max_iterations=N_HYP)
+    threads = max(1, min(os.cpu_count() or 1, 8))      # reference parallelism = its 8-worker pool over instances
+    rows, hyps = 512, 2048
+    cache = {}
+    for _ in range(args.warmup):
+        cpu_rate(case, threads, 16, 32, cache)
+    vals, wall = [], 0.0
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        v, tm, tr, full_s = cpu_rate(case, threads, rows, hyps, cache)
+        wall += time.perf_counter() - t0
+        vals.append(v)
+    value = float(np.mean(vals))
+    sample = (f"per step and per thread: first {rows} source rows x all {N_TGT} targets (matching) + first {hyps} hypotheses "
+              f"x all {N_SRC} correspondences (RANSAC), extrapolated linearly to the full job; {threads} independent "
+              f"single-threaded registrations in parallel (the reference's only parallelism, pipeline.cpp:321-327)")
+    line = {
+        "impl": "reference", "metric": "ransac_hyp_per_s", "value": value, "unit": "hyp/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "n_src": N_SRC, "n_tgt": N_TGT, "hypotheses": N_HYP},
+        "cpu_baseline": {"value": value, "unit": "hyp/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "hyp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "extrapolated_full_step_ms": 1e3 * threads * N_HYP / value,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- ours
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank, local_rank, world = dist_env()
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    else:
+        torch.cuda.set_device(0)
+    dev = torch.cuda.current_device()
+    b3d = importlib.import_module("3dvision_b200")
+    bdist = importlib.import_module("3dvision_b200.dist")
+    syn = b3d.synthetic
+    if not b3d.cuda_available():
+        raise SystemExit("bench.py: no sm_100 CUDA device and no CPU fallback")
+
+    case = syn.ransac_case(n_src=N_SRC, n_tgt=N_TGT, max_iterations=N_HYP)
+    ctx = b3d.Context(dev)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+
+    # resident inputs (value) ---------------------------------------------------------
+    d_src = torch.from_numpy(case.source).cuda(); d_tgt = torch.from_numpy(case.target).cuda()
+    d_sd = torch.from_numpy(case.source_desc).cuda(); d_td = torch.from_numpy(case.target_desc).cuda()
+    ctx.set_clouds_device(d_src.data_ptr(), N_SRC, d_tgt.data_ptr(), None, N_TGT)
+    ctx.set_features_device(d_sd.data_ptr(), d_td.data_ptr())
+    backend = bdist.CudaBackend(ctx, N_SRC)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")       # > 126 MB L2
+    confidence = 2.0                                                        # never exits early: all H hypotheses scored
+
+    def step_resident():
+        return bdist.sharded_ransac(backend, case.voxel_size, N_HYP, confidence)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(dev)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.kernel_launches
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    stage_acc = np.zeros(4)
+    result = None
+    for i in range(args.steps):
+        flush.zero_()
+        barrier()
+        ev[i][0].record()
+        result = step_resident()
+        ev[i][1].record()
+        torch.cuda.synchronize()
+        stage_acc += [ctx.stage_ms(s) for s in range(4)]
+    barrier()
+    launches = ctx.kernel_launches - launches0
+    clocks = sampler.stop() if rank == 0 else {}
+    my_ms = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([my_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    value = N_HYP * args.steps / (total_ms * 1e-3)
+
+    # end to end through the C-ABI with pinned host buffers -------------------------------
+    keep = [pinned(case.source), pinned(case.target), pinned(case.source_desc), pinned(case.target_desc)]
+    h_src, h_tgt, h_sd, h_td = (k[1] for k in keep)
+    h2d = h_src.nbytes + h_tgt.nbytes + h_sd.nbytes + h_td.nbytes
+    d2h = 80
+
+    def step_e2e():
+        if world == 1:
+            return ctx.ransac(h_src, h_tgt, h_sd, h_td, case.voxel_size, N_HYP, confidence)
+        ctx.set_clouds(h_src, h_tgt)
+        ctx.set_features(h_sd, h_td)
+        return bdist.sharded_ransac(backend, case.voxel_size, N_HYP, confidence)
+
+    step_e2e()
+    barrier()
+    e2e_s = 0.0
+    for _ in range(args.steps):
+        flush.zero_()
+        barrier()
+        t0 = time.perf_counter()
+        result_e2e = step_e2e()
+        torch.cuda.synchronize()
+        e2e_s += time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = N_HYP * args.steps / float(te.item())
+    assert np.array_equal(result[0], result_e2e[0]), "resident and host-buffer paths disagree"
+    # restore resident pointers for anything that follows
+    ctx.set_clouds_device(d_src.data_ptr(), N_SRC, d_tgt.data_ptr(), None, N_TGT)
+    ctx.set_features_device(d_sd.data_ptr(), d_td.data_ptr())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # roofline of the dominant kernel (inlier scoring) -----------------------------------
+    h0, h1 = bdist.shard_range(N_HYP, rank, world)
+    score_ms = stage_acc[2] / args.steps
+    achieved = OPS_PER_PAIR * (h1 - h0) * float(N_SRC) / (score_ms * 1e-3) / 1e12
+    peak = ctx.measure_fp32_rate() / 1e12
+    roofline = {
+        "bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+        "kernel": "score_exact_kernel", "kernel_ms": score_ms,
+        "note": ("SURVEY.md §8(d): RANSAC scoring is FP32 CUDA-core issue bound (not HBM, not tensor). achieved = 28 un-fused "
+                 "fp32 ops x hypotheses x correspondences per launch / CUDA-event kernel time; peak = un-fused FMUL+FADD issue "
+                 "rate measured live on this GPU by b3d_measure_fp32_rate (MEASURED_PEAKS.json has no fp32 figure)"),
+    }
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        roofline["hbm_peak_gbs_measured"] = peaks.get("hbm_gbs")
+    except Exception:
+        pass
+
+    line = {
+        "metric": "ransac_hyp_per_s", "value": value, "unit": "hyp/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "n_src": N_SRC, "n_tgt": N_TGT, "hypotheses": N_HYP, "confidence": confidence,
+                   "l2": "flushed (256 MiB write) between timed steps", "sharding": f"rows+hypotheses/{world}"},
+        "clocks": {"sm_mhz": clocks.get("sm_mhz"), "sm_max_mhz": clocks.get("sm_max_mhz"), "reasons": clocks.get("reasons", [])},
+        "e2e": {"value": e2e_value, "unit": "hyp/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "stages_ms": {"match": stage_acc[0] / args.steps, "prepare": stage_acc[1] / args.steps,
+                      "score": stage_acc[2] / args.steps, "select_finish": stage_acc[3] / args.steps},
+        "result": {"fitness": result[1], "rmse": result[2], "best_iteration": result[3]},
+    }
+
+    if world == 1:
+        line["also"] = secondary(ctx, b3d, syn, case, flush)
+        cache = {}
+        t0 = time.perf_counter()
+        v, tm, tr, full_s = cpu_rate(case, 1, 512, 2048, cache)
+        line["cpu_baseline"] = {
+            "value": v, "unit": "hyp/s", "cores": 1, "kind": "port",
+            "sample": (f"oracle (CPU restatement of registration.cpp:204-295), one thread: first 512 source rows x {N_TGT} targets "
+                       f"({tm:.2f} s) + first 2048 hypotheses x {N_SRC} correspondences ({tr:.2f} s), extrapolated linearly to the "
+                       f"full job ({full_s:.0f} s); host has {os.cpu_count()} cores"),
+        }
+    print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def secondary(ctx, b3d, syn, case, flush):
+    """N=1 only: the other two figures of BASELINE.json's metric."""
+    import torch
+    out = {}
+    # ICP iterations/s, configs[1]: 300k scene vs 100k model, point-to-plane, exactly 50 iterations
+    ic = syn.icp_case()
+    ctx.set_clouds(ic.source, ic.target, ic.target_normals)
+    ctx.icp_run(ic.T_init, ic.threshold, 5, True, False)
+    torch.cuda.synchronize()
+    reps, ms = 3, 0.0
+    for _ in range(reps):
+        flush.zero_(); torch.cuda.synchronize()
+        T, fit, rmse, iters = ctx.icp_run(ic.T_init, ic.threshold, ic.iterations, True, False)
+        ms += ctx.stage_ms(5)
+    ms /= reps
+    out["icp"] = {"workload": "configs[1]: 300k-point scene vs 100k-point model, point-to-plane, 50 iterations (no convergence break)",
+                  "iters_per_s": ic.iterations / (ms * 1e-3), "ms_per_iteration": ms / ic.iterations,
+                  "grid_build_ms": ctx.stage_ms(4), "fitness": fit, "rmse": rmse,
+                  "rot_err_vs_truth": syn.rotation_error(T, ic.T_true), "trans_err_vs_truth": syn.translation_error(T, ic.T_true)}
+    # full registration with the reference's default budget: H = 100 000, confidence 0.999, ICP <= 200 iterations
+    tgt_normals = case.target_normals
+    keep = [pinned(case.source), pinned(case.target), pinned(case.source_desc), pinned(case.target_desc), pinned(tgt_normals)]
+    h_src, h_tgt, h_sd, h_td, h_n = (k[1] for k in keep)
+
+    def full():
+        T0, f0, r0, _ = ctx.ransac(h_src, h_tgt, h_sd, h_td, case.voxel_size, 100_000, 0.999)
+        return ctx.icp(h_src, h_tgt, h_n, T0, case.voxel_size * 0.4, 200, True), (f0, r0)
+
+    full()
+    torch.cuda.synchronize()
+    t = []
+    for _ in range(3):
+        flush.zero_(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        (T, fit, rmse, iters), (f0, r0) = full()
+        t.append(time.perf_counter() - t0)
+    out["registration"] = {"workload": "1M-point scene -> 100k source points vs 100k model: ransacRegistration(H=100000, conf 0.999) + "
+                                       "icpRefine(thr 0.4*voxel, <=200 it, point-to-plane), host buffers in, pose out",
+                           "ms": 1e3 * float(np.median(t)), "ransac_fitness": f0, "icp_fitness": fit, "icp_iterations": iters,
+                           "rot_err_vs_truth": syn.rotation_error(T, case.T_true),
+                           "trans_err_vs_truth": syn.translation_error(T, case.T_true)}
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

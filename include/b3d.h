@@ -149,6 +149,11 @@ uint64_t b3d_kernel_launches(const b3d_ctx* ctx);
  * 4 icp grid build, 5 icp iterations. Returns -1 for an unknown stage. */
 float b3d_stage_ms(const b3d_ctx* ctx, int stage);
 
+/* Measures the sustained issue rate of separate (un-fused) FMUL + FADD instructions on this
+ * device, in lane-operations per second: the roofline denominator of the scoring kernel, whose
+ * arithmetic must not be contracted into FMAs (reference build: no FMA, README.md:13). */
+int b3d_measure_fp32_rate(b3d_ctx* ctx, double* out_ops_per_second);
+
 #ifdef __cplusplus
 }
 #endif
