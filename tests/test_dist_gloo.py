@@ -1,0 +1,119 @@
+"""world_size-2 gloo tests of the hypothesis/row sharding protocol (3dvision_b200/dist.py) on CPU.
+
+The CUDA context is replaced by a stand-in that answers each backend call from the oracle, so the
+code under test is exactly the host-side protocol the NCCL path runs: disjoint-slice all-reduce of
+correspondences, the packed (fitness, id) MAX key, and the early-exit restriction."""
+import importlib
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+bdist = importlib.import_module("3dvision_b200.dist")
+syn = importlib.import_module("3dvision_b200.synthetic")
+
+
+class OracleBackend:
+    def __init__(self, case):
+        from oracle import oracle as O
+        self.O = O; self.case = case; self.n_src = case.source.shape[0]
+        self.keys = torch.zeros(2, dtype=torch.int64)
+
+    def match_rows(self, r0, r1):
+        corr = np.zeros(self.n_src, np.int32)
+        if r1 > r0:
+            corr[r0:r1] = self.O.match_features(self.case.source_desc, self.case.target_desc, r0, r1).astype(np.int32)
+        self._corr_t = torch.from_numpy(corr)
+        return self._corr_t
+
+    def correspondences_ready(self):
+        self.corr = self._corr_t.numpy().astype(np.uint32)
+
+    def prepare(self, voxel, H, confidence):
+        self.voxel, self.H, self.conf = voxel, H, confidence
+
+    def score(self, h0, h1):
+        r = self.O.ransac(self.case.source, self.case.target, self.corr, self.voxel, self.H, 2.0, iter_lo=h0, iter_hi=h1, want_counts=True)
+        self.counts = r.extra["counts"]
+
+    def reduce(self, h0, h1, with_limit):
+        n = np.float32(self.n_src)
+        limit = 0xFFFFFFFF
+        if with_limit and int(self.keys[1]) != 0:
+            limit = 0xFFFFFFFF - int(self.keys[1])
+        best, exit_key = 0, 0
+        for h in range(h0, h1):
+            c = int(self.counts[h])
+            if c <= 0:
+                continue
+            fit = np.float32(c) / n
+            if not with_limit and fit > np.float32(self.conf):
+                exit_key = max(exit_key, bdist.pack_exit_key(h))
+        if not with_limit:
+            self.keys[1] = exit_key
+            if exit_key:
+                limit = 0xFFFFFFFF - exit_key
+        for h in range(h0, h1):
+            c = int(self.counts[h])
+            if c > 0 and h <= limit:
+                best = max(best, bdist.pack_best_key(np.float32(c) / n, h))
+        self.keys[0] = best
+        return self.keys
+
+    def finish(self):
+        fit, hid = bdist.unpack_best_key(int(self.keys[0]))
+        if hid < 0:
+            return np.eye(4, dtype=np.float32), 0.0, 0.0, -1
+        ok, R, t, _ = self.O.ransac_hypothesis(self.case.source, self.case.target, self.corr, hid)
+        T = np.eye(4, dtype=np.float32); T[:3, :3] = R; T[:3, 3] = t
+        return T, fit, None, hid
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, confidence, H, seed):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import oracle as O
+        case = syn.ransac_case(n_src=600, n_tgt=500, seed=seed, max_iterations=H)
+        T, fit, _, best = bdist.sharded_ransac(OracleBackend(case), case.voxel_size, H, confidence)
+        ref = O.ransac_registration(case.source, case.target, case.source_desc, case.target_desc, case.voxel_size, H, confidence)
+        corr = O.match_features(case.source_desc, case.target_desc)
+        ref2 = O.ransac(case.source, case.target, corr, case.voxel_size, H, confidence)
+        assert best == ref2.extra["best_iter"], (rank, best, ref2.extra["best_iter"])
+        assert np.array_equal(T, ref.transformation) and np.float32(fit) == np.float32(ref.fitness)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("confidence,H,seed", [(2.0, 700, 1),      # no early exit: plain (max fitness, min id)
+                                                (0.30, 700, 1),     # exit id inside one rank's shard restricts the other's
+                                                (0.05, 700, 2),     # exits almost immediately (rank 0's shard)
+                                                (0.999, 3, 3)])     # fewer hypotheses than would fill both shards evenly
+def test_sharded_ransac_matches_sequential_reference(confidence, H, seed):
+    mp.spawn(_worker, args=(2, _free_port(), confidence, H, seed), nprocs=2, join=True)
+
+
+def test_shard_range_partitions_exactly():
+    for total in (0, 1, 7, 100, 1_000_000):
+        for world in (1, 2, 3, 8):
+            r = [bdist.shard_range(total, k, world) for k in range(world)]
+            assert r[0][0] == 0 and r[-1][1] == total
+            assert all(r[k][1] == r[k + 1][0] for k in range(world - 1))
+            assert max(b - a for a, b in r) - min(b - a for a, b in r) <= 1
+
+
+def test_key_packing_orders_like_the_sequential_rule():
+    """MAX over keys == strict '>' on fitness with the earliest id winning (registration.cpp:284)."""
+    k = bdist.pack_best_key
+    assert k(0.5, 10) > k(0.25, 3) and k(0.5, 3) > k(0.5, 10)
+    assert bdist.unpack_best_key(k(0.7001799941062927, 21264)) == (float(np.float32(0.7001799941062927)), 21264)
+    assert bdist.unpack_best_key(0) == (0.0, -1)
+    assert bdist.pack_exit_key(5) > bdist.pack_exit_key(9)          # MAX picks the earliest exit
