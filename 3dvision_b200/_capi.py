@@ -173,6 +173,7 @@ class Context:
         if sd.shape[0] != src.shape[0] or td.shape[0] != tgt.shape[0]:
             raise ValueError("descriptor rows must match cloud sizes")
         T = np.empty(16, np.float32); fit = C.c_float(); rm = C.c_float(); best = C.c_int32()
+        self._n_src, self._n_tgt, self._H = src.shape[0], tgt.shape[0], max_iterations
         self._check(self._L.b3d_ransac(self._h, _ptr(src), src.shape[0], _ptr(tgt), tgt.shape[0], _ptr(sd), _ptr(td),
                                        voxel_size, max_iterations, confidence,
                                        T.ctypes.data_as(_f32p), C.byref(fit), C.byref(rm), C.byref(best)))
@@ -185,6 +186,7 @@ class Context:
             nrm = None                      # PointCloud::hasNormals() false, registration.hpp:17
         T0c = _T_colmajor(T0)
         T = np.empty(16, np.float32); fit = C.c_float(); rm = C.c_float(); it = C.c_int32()
+        self._n_src, self._n_tgt = src.shape[0], tgt.shape[0]
         self._check(self._L.b3d_icp(self._h, _ptr(src), src.shape[0], _ptr(tgt), _ptr(nrm), tgt.shape[0],
                                     T0c.ctypes.data_as(_f32p), distance_threshold, max_iterations, int(bool(point_to_plane)),
                                     T.ctypes.data_as(_f32p), C.byref(fit), C.byref(rm), C.byref(it)))

@@ -45,6 +45,8 @@ constexpr float kCoordLimit = 65536.0f;     // |cell coordinate| bound that keep
 
 struct GridParams {
     float inv_cell;
+    float cell;                 // 1 / inv_cell
+    float slack;                // conservative bound on how far a point can sit outside its nominal cell (rounding)
     unsigned mask;              // capacity - 1
     unsigned max_abs_bits;      // max |coordinate| over the target, as float bits
     unsigned n_points;
@@ -85,6 +87,8 @@ __global__ void grid_init_kernel(CellSlot* slots, unsigned capacity, GridParams*
         float inv = (cell > 0.0f) ? 1.0f / cell : INFINITY;
         float inv_cap = (max_abs > 0.0f) ? kCoordLimit / max_abs : kCoordLimit;
         gp->inv_cell = fminf(inv, inv_cap);
+        gp->cell = 1.0f / gp->inv_cell;
+        gp->slack = max_abs * 4.76837158e-7f;            // 2^-21 * max|coordinate|: > 4 ulp of any coordinate
         gp->mask = capacity - 1u;
         gp->n_points = n_points;
     }
@@ -132,32 +136,68 @@ __global__ void grid_scatter_kernel(const float4* __restrict__ pts, const float4
     }
 }
 
-// nearest target of p within the 27-cell neighbourhood: lexicographic (d2, index) minimum
-__device__ __forceinline__ void grid_nearest(float px, float py, float pz, const CellSlot* __restrict__ slots,
-                                             const float4* __restrict__ gpts, float inv, unsigned mask,
+struct GridView {
+    const CellSlot* __restrict__ slots;
+    const float4* __restrict__ pts;
+    float inv, cell, slack;
+    unsigned mask;
+};
+__device__ __forceinline__ GridView make_view(const CellSlot* slots, const float4* pts, const GridParams* __restrict__ gp) {
+    GridView g; g.slots = slots; g.pts = pts; g.inv = gp->inv_cell; g.cell = gp->cell; g.slack = gp->slack; g.mask = gp->mask;
+    return g;
+}
+
+__device__ __forceinline__ void visit_cell(const GridView& g, int cx, int cy, int cz, float px, float py, float pz,
+                                           float& best_d2, unsigned& best_idx, unsigned& best_pos) {
+    const unsigned long long key = pack_cell(cx, cy, cz);
+    unsigned slot = hash_cell(key) & g.mask;
+    unsigned start = 0, count = 0;
+    while (true) {
+        const CellSlot s = g.slots[slot];
+        if (s.key == key) { start = s.start; count = s.count; break; }
+        if (s.key == kEmptyKey) break;
+        slot = (slot + 1u) & g.mask;
+    }
+    auto consider = [&](const float4 q, unsigned pos) {
+        float e0 = px - q.x, e1 = py - q.y, e2 = pz - q.z;
+        float d2 = e0 * e0 + (e1 * e1 + e2 * e2);                  // (p - q).squaredNorm()
+        unsigned idx = __float_as_uint(q.w);
+        if (d2 < best_d2 || (d2 == best_d2 && idx < best_idx)) { best_d2 = d2; best_idx = idx; best_pos = pos; }
+    };
+    unsigned k = 0;
+    for (; k + 4 <= count; k += 4) {                               // four independent loads in flight
+        const float4 q0 = g.pts[start + k], q1 = g.pts[start + k + 1], q2 = g.pts[start + k + 2], q3 = g.pts[start + k + 3];
+        consider(q0, start + k); consider(q1, start + k + 1); consider(q2, start + k + 2); consider(q3, start + k + 3);
+    }
+    for (; k < count; ++k) consider(g.pts[start + k], start + k);
+}
+
+// Nearest target of p within the 27-cell neighbourhood: lexicographic (d2, index) minimum.
+// The query's own cell is searched first; a neighbour cell is skipped when even its nearest face
+// (shrunk by `slack` to cover rounding in the cell assignment) is farther than the best match so
+// far, which cannot change the minimum or its tie-break.
+__device__ __forceinline__ void grid_nearest(float px, float py, float pz, const GridView& g,
                                              float& best_d2, unsigned& best_idx, unsigned& best_pos) {
     best_d2 = FLT_MAX; best_idx = B3D_NO_MATCH; best_pos = 0u;
-    const int cx = cell_coord(px, inv), cy = cell_coord(py, inv), cz = cell_coord(pz, inv);
-    for (int dz = -1; dz <= 1; ++dz)
-        for (int dy = -1; dy <= 1; ++dy)
+    const int cx = cell_coord(px, g.inv), cy = cell_coord(py, g.inv), cz = cell_coord(pz, g.inv);
+    visit_cell(g, cx, cy, cz, px, py, pz, best_d2, best_idx, best_pos);
+    // distance from p to the low / high faces of its cell along each axis, made conservative
+    const float lox = fmaxf(px - (float)cx * g.cell - g.slack, 0.0f), hix = fmaxf((float)(cx + 1) * g.cell - px - g.slack, 0.0f);
+    const float loy = fmaxf(py - (float)cy * g.cell - g.slack, 0.0f), hiy = fmaxf((float)(cy + 1) * g.cell - py - g.slack, 0.0f);
+    const float loz = fmaxf(pz - (float)cz * g.cell - g.slack, 0.0f), hiz = fmaxf((float)(cz + 1) * g.cell - pz - g.slack, 0.0f);
+    for (int dz = -1; dz <= 1; ++dz) {
+        const float gz = dz < 0 ? loz : (dz > 0 ? hiz : 0.0f);
+        for (int dy = -1; dy <= 1; ++dy) {
+            const float gy = dy < 0 ? loy : (dy > 0 ? hiy : 0.0f);
             for (int dx = -1; dx <= 1; ++dx) {
-                const unsigned long long key = pack_cell(cx + dx, cy + dy, cz + dz);
-                unsigned slot = hash_cell(key) & mask;
-                unsigned start = 0, count = 0;
-                while (true) {
-                    const CellSlot s = slots[slot];
-                    if (s.key == key) { start = s.start; count = s.count; break; }
-                    if (s.key == kEmptyKey) break;
-                    slot = (slot + 1u) & mask;
-                }
-                for (unsigned k = 0; k < count; ++k) {
-                    const float4 q = gpts[start + k];
-                    float e0 = px - q.x, e1 = py - q.y, e2 = pz - q.z;
-                    float d2 = e0 * e0 + (e1 * e1 + e2 * e2);          // (p - q).squaredNorm()
-                    unsigned idx = __float_as_uint(q.w);
-                    if (d2 < best_d2 || (d2 == best_d2 && idx < best_idx)) { best_d2 = d2; best_idx = idx; best_pos = start + k; }
-                }
+                if ((dx | dy | dz) == 0) continue;
+                const float gx = dx < 0 ? lox : (dx > 0 ? hix : 0.0f);
+                const float gap2 = __fmul_rd(gx, gx) + (__fmul_rd(gy, gy) + __fmul_rd(gz, gz));
+                if (gap2 * 0.999f > best_d2) continue;
+                visit_cell(g, cx + dx, cy + dy, cz + dz, px, py, pz, best_d2, best_idx, best_pos);
             }
+        }
+    }
 }
 
 __device__ __forceinline__ void load_Rt(const float* __restrict__ T, float R[9], float t[3]) {
@@ -180,11 +220,11 @@ __global__ void icp_nearest_kernel(const float4* __restrict__ src, unsigned n_sr
                                    const GridParams* __restrict__ gp, uint32_t* __restrict__ out_idx, float* __restrict__ out_d2) {
     float R[9], t[3];
     load_Rt(T, R, t);
-    const float inv = gp->inv_cell; const unsigned mask = gp->mask;
+    const GridView g = make_view(slots, gpts, gp);
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n_src; i += gridDim.x * blockDim.x) {
         float x, y, z; transform_point(R, t, src[i], x, y, z);
         float d2; unsigned idx, pos;
-        grid_nearest(x, y, z, slots, gpts, inv, mask, d2, idx, pos);
+        grid_nearest(x, y, z, g, d2, idx, pos);
         if (idx != B3D_NO_MATCH && sqrtf(d2) > thr) { idx = B3D_NO_MATCH; }
         out_idx[i] = idx;
         out_d2[i] = (idx == B3D_NO_MATCH) ? FLT_MAX : d2;
@@ -200,99 +240,148 @@ constexpr int kAccPoint = 16;     // 3 (sum p) + 3 (sum q) + 9 (sum p q^T) + 1 (
 constexpr int kAccMax = 28;
 constexpr int kPartialStride = 32;   // doubles per block partial: kAccMax values + count
 
+// Block-wide sum of one contribution vector per thread: fp64 from the first addition on.
 template <int NV>
-__device__ __forceinline__ void block_reduce_store(double (&acc)[NV], int n_corr, double* __restrict__ partial_out) {
+__device__ __forceinline__ void block_reduce_store(const float (&contrib)[NV], int n_corr, double* __restrict__ partial_out) {
     __shared__ double red[kIcpThreads / 32][kAccMax + 1];
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double cnt = (double)n_corr;
 #pragma unroll
-    for (int s = 16; s >= 1; s >>= 1) {
+    for (int v = 0; v < NV; ++v) {
+        double a = (double)contrib[v];
 #pragma unroll
-        for (int v = 0; v < NV; ++v) acc[v] += __shfl_xor_sync(0xffffffffu, acc[v], s);
-        cnt += __shfl_xor_sync(0xffffffffu, cnt, s);
+        for (int s = 16; s >= 1; s >>= 1) a += __shfl_xor_sync(0xffffffffu, a, s);
+        if (lane == 0) red[warp][v] = a;
     }
-    if (lane == 0) {
+    {
+        int cnt = n_corr;
 #pragma unroll
-        for (int v = 0; v < NV; ++v) red[warp][v] = acc[v];
-        red[warp][kAccMax] = cnt;
+        for (int s = 16; s >= 1; s >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, s);
+        if (lane == 0) red[warp][kAccMax] = (double)cnt;
     }
     __syncthreads();
-    if (threadIdx.x <= kAccMax) {
+    if (threadIdx.x < kPartialStride) {
         const int v = threadIdx.x;
+        double s = 0.0;
         if (v < NV || v == kAccMax) {
-            double s = 0.0;
 #pragma unroll
             for (int w = 0; w < kIcpThreads / 32; ++w) s += red[w][v];
-            partial_out[v] = s;
         }
+        partial_out[v] = s;
     }
 }
 
+// One query per thread: the search phase needs few registers, so occupancy (and with it the
+// number of hash probes and cell reads in flight) is high; the per-point terms are formed in
+// fp32 exactly as the reference forms them and enter fp64 at the first addition.
 template <bool PLANE>
-__global__ void __launch_bounds__(kIcpThreads)
+__global__ void __launch_bounds__(kIcpThreads, 4)
 icp_accumulate_kernel(const float4* __restrict__ src, unsigned n_src, const DeviceState* __restrict__ st, float thr,
                       const CellSlot* __restrict__ slots, const float4* __restrict__ gpts, const float4* __restrict__ gnrm,
                       const GridParams* __restrict__ gp, double* __restrict__ partials) {
     if (st->done) return;
-    float R[9], t[3];
-    load_Rt(st->T, R, t);
-    const float inv = gp->inv_cell; const unsigned mask = gp->mask;
     constexpr int NV = PLANE ? kAccPlane : kAccPoint;
-    double acc[NV];
-#pragma unroll
-    for (int v = 0; v < NV; ++v) acc[v] = 0.0;
+    // ---- search phase (few live registers) ----
+    float x = 0.f, y = 0.f, z = 0.f, d2 = 0.f;
+    unsigned pos = 0;
     int n_corr = 0;
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n_src; i += gridDim.x * blockDim.x) {
-        float x, y, z; transform_point(R, t, src[i], x, y, z);
-        float d2; unsigned idx, pos;
-        grid_nearest(x, y, z, slots, gpts, inv, mask, d2, idx, pos);
-        if (idx == B3D_NO_MATCH) continue;
-        if (sqrtf(d2) > thr) continue;                     // registration.cpp:337-338 (d == thr is kept)
-        ++n_corr;
-        const float4 q = gpts[pos];
-        if (PLANE) {
-            const float4 n = gnrm[pos];
-            float J[6];
-            J[0] = y * n.z - z * n.y;                      // p.cross(n), registration.cpp:346
-            J[1] = z * n.x - x * n.z;
-            J[2] = x * n.y - y * n.x;
-            J[3] = n.x; J[4] = n.y; J[5] = n.z;
-            float r = (x - q.x) * n.x + ((y - q.y) * n.y + (z - q.z) * n.z);   // (p - q).dot(n)
-            int k = 0;
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_src) {
+        float R[9], t[3];
+        load_Rt(st->T, R, t);
+        const GridView g = make_view(slots, gpts, gp);
+        transform_point(R, t, src[i], x, y, z);
+        unsigned idx;
+        grid_nearest(x, y, z, g, d2, idx, pos);
+        n_corr = (idx != B3D_NO_MATCH && !(sqrtf(d2) > thr)) ? 1 : 0;       // registration.cpp:337-338 (d == thr is kept)
+    }
+    // ---- contribution phase ----
+    float c[NV];
+    if (!n_corr) { x = 0.f; y = 0.f; z = 0.f; d2 = 0.f; }      // unmatched (or NaN) queries contribute exact zeros
+    const float keep = n_corr ? 1.0f : 0.0f;
+    const float4 q = n_corr ? gpts[pos] : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (PLANE) {
+        const float4 n = n_corr ? gnrm[pos] : make_float4(0.f, 0.f, 0.f, 0.f);
+        float J[6];
+        J[0] = y * n.z - z * n.y;                              // p.cross(n), registration.cpp:346
+        J[1] = z * n.x - x * n.z;
+        J[2] = x * n.y - y * n.x;
+        J[3] = n.x; J[4] = n.y; J[5] = n.z;
+        float r = (x - q.x) * n.x + ((y - q.y) * n.y + (z - q.z) * n.z);       // (p - q).dot(n)
+        int k = 0;
 #pragma unroll
-            for (int a = 0; a < 6; ++a)
+        for (int a = 0; a < 6; ++a)
 #pragma unroll
-                for (int b = a; b < 6; ++b) acc[k++] += (double)(J[a] * J[b]);   // fp32 product, as the reference forms it
+            for (int b = a; b < 6; ++b) c[k++] = J[a] * J[b];                  // zero normal => zero terms when unmatched
 #pragma unroll
-            for (int a = 0; a < 6; ++a) acc[21 + a] += (double)(J[a] * r);
-            acc[27] += (double)d2;
-        } else {
-            acc[0] += (double)x; acc[1] += (double)y; acc[2] += (double)z;
-            acc[3] += (double)q.x; acc[4] += (double)q.y; acc[5] += (double)q.z;
-            const double p[3] = {(double)x, (double)y, (double)z};
-            const double qq[3] = {(double)q.x, (double)q.y, (double)q.z};
+        for (int a = 0; a < 6; ++a) c[21 + a] = J[a] * r;
+        c[27] = d2 * keep;
+    } else {
+        c[0] = x * keep; c[1] = y * keep; c[2] = z * keep; c[3] = q.x; c[4] = q.y; c[5] = q.z;
 #pragma unroll
-            for (int a = 0; a < 3; ++a)
+        for (int v = 6; v < 15; ++v) c[v] = 0.0f;
+        c[15] = d2 * keep;
+    }
+    if (PLANE) {
+        block_reduce_store<NV>(c, n_corr, partials + (size_t)blockIdx.x * kPartialStride);
+    } else {
+        // point-to-point: sum p, sum q, sum p q^T (exact fp64 products), sum d2
+        __shared__ double red[kIcpThreads / 32][kAccMax + 1];
+        const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const double p[3] = {(double)c[0], (double)c[1], (double)c[2]}, q[3] = {(double)c[3], (double)c[4], (double)c[5]};
+        double vals[kAccPoint];
 #pragma unroll
-                for (int b = 0; b < 3; ++b) acc[6 + a * 3 + b] += p[a] * qq[b];
-            acc[15] += (double)d2;
+        for (int a = 0; a < 3; ++a) { vals[a] = p[a]; vals[3 + a] = q[a]; }
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int b = 0; b < 3; ++b) vals[6 + a * 3 + b] = p[a] * q[b];
+        vals[15] = (double)c[15];
+#pragma unroll
+        for (int v = 0; v < kAccPoint; ++v) {
+            double a = vals[v];
+#pragma unroll
+            for (int s = 16; s >= 1; s >>= 1) a += __shfl_xor_sync(0xffffffffu, a, s);
+            if (lane == 0) red[warp][v] = a;
+        }
+        int cnt = n_corr;
+#pragma unroll
+        for (int s = 16; s >= 1; s >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, s);
+        if (lane == 0) red[warp][kAccMax] = (double)cnt;
+        __syncthreads();
+        if (threadIdx.x < kPartialStride) {
+            const int v = threadIdx.x;
+            double s = 0.0;
+            if (v < kAccPoint || v == kAccMax) {
+#pragma unroll
+                for (int w = 0; w < kIcpThreads / 32; ++w) s += red[w][v];
+            }
+            partials[(size_t)blockIdx.x * kPartialStride + v] = s;
         }
     }
-    block_reduce_store<NV>(acc, n_corr, partials + (size_t)blockIdx.x * kPartialStride);
 }
 
 // one block: fixed-order sum of the block partials, solve, update T / result / flags
+constexpr int kUpdateThreads = 256;
 template <bool PLANE>
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(kUpdateThreads)
 icp_update_kernel(const double* __restrict__ partials, int n_blocks, int iter, float n_src_f, int stop_on_convergence,
                   DeviceState* __restrict__ st) {
     if (st->done) return;
+    // fixed-order (hence run-to-run deterministic) sum of the block partials: 8 strided groups, then 8 -> 1
+    __shared__ double grp[kUpdateThreads / kPartialStride][kPartialStride];
     __shared__ double tot[kPartialStride];
-    const int v = threadIdx.x;
-    if (v < kPartialStride) {
+    {
+        const int v = threadIdx.x % kPartialStride, gidx = threadIdx.x / kPartialStride;
         double s = 0.0;
-        for (int b = 0; b < n_blocks; ++b) s += partials[(size_t)b * kPartialStride + v];
-        tot[v] = s;
+        for (int b = gidx; b < n_blocks; b += kUpdateThreads / kPartialStride) s += partials[(size_t)b * kPartialStride + v];
+        grp[gidx][v] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < kPartialStride) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < kUpdateThreads / kPartialStride; ++k) s += grp[k][threadIdx.x];
+        tot[threadIdx.x] = s;
     }
     __syncthreads();
     if (threadIdx.x != 0) return;
@@ -405,7 +494,7 @@ int icp_run_impl(b3d_ctx* c, const float* T0, float thr, int max_iter, int p2pla
     B3D_LAUNCHED(c);
 
     const unsigned n_src = (unsigned)c->n_src;
-    const int blocks = grid_for(n_src, kIcpThreads, 4);
+    const int blocks = div_up(n_src, kIcpThreads);           // one query per thread
     B3D_CUDA(c, c->partials.ensure(sizeof(double) * kPartialStride * (size_t)blocks));
     {
         StageTimer timer(c, 5);
@@ -415,13 +504,13 @@ int icp_run_impl(b3d_ctx* c, const float* T0, float thr, int max_iter, int p2pla
                 icp_accumulate_kernel<true><<<blocks, kIcpThreads, 0, c->stream>>>(c->src4.as<float4>(), n_src, st, thr, slots, c->grid_pts.as<float4>(),
                                                                                    c->grid_nrm.as<float4>(), gp, c->partials.as<double>());
                 B3D_LAUNCHED(c);
-                icp_update_kernel<true><<<1, 64, 0, c->stream>>>(c->partials.as<double>(), blocks, iter, (float)c->n_src, stop_on_conv, st);
+                icp_update_kernel<true><<<1, kUpdateThreads, 0, c->stream>>>(c->partials.as<double>(), blocks, iter, (float)c->n_src, stop_on_conv, st);
                 B3D_LAUNCHED(c);
             } else {
                 icp_accumulate_kernel<false><<<blocks, kIcpThreads, 0, c->stream>>>(c->src4.as<float4>(), n_src, st, thr, slots, c->grid_pts.as<float4>(),
                                                                                     c->grid_nrm.as<float4>(), gp, c->partials.as<double>());
                 B3D_LAUNCHED(c);
-                icp_update_kernel<false><<<1, 64, 0, c->stream>>>(c->partials.as<double>(), blocks, iter, (float)c->n_src, stop_on_conv, st);
+                icp_update_kernel<false><<<1, kUpdateThreads, 0, c->stream>>>(c->partials.as<double>(), blocks, iter, (float)c->n_src, stop_on_conv, st);
                 B3D_LAUNCHED(c);
             }
             // poll the device-side done flag now and then so converged runs stop launching
