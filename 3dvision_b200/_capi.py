@@ -27,7 +27,7 @@ NO_MATCH = 0xFFFFFFFF
 SYMBOLS = [
     "b3d_cuda_available", "b3d_ctx_create", "b3d_ctx_destroy", "b3d_ctx_set_stream", "b3d_strerror", "b3d_last_error",
     "b3d_ransac", "b3d_icp",
-    "b3d_set_clouds", "b3d_set_features", "b3d_match_features", "b3d_get_correspondences", "b3d_set_correspondences",
+    "b3d_set_clouds", "b3d_set_features", "b3d_set_match_mode", "b3d_match_features", "b3d_get_correspondences", "b3d_set_correspondences",
     "b3d_correspondences_devptr", "b3d_ransac_prepare", "b3d_ransac_score", "b3d_ransac_reduce", "b3d_ransac_finish",
     "b3d_ransac_counts", "b3d_ransac_hypotheses", "b3d_icp_run", "b3d_icp_nearest",
     "b3d_kernel_launches", "b3d_stage_ms", "b3d_measure_fp32_rate",
@@ -78,6 +78,7 @@ def _declare(L):
     L.b3d_set_clouds.argtypes = [_vp, _vp, C.c_size_t, _vp, _vp, C.c_size_t, C.c_int]
     L.b3d_set_features.argtypes = [_vp, _vp, _vp, C.c_int]
     L.b3d_match_features.argtypes = [_vp, C.c_size_t, C.c_size_t]
+    L.b3d_set_match_mode.argtypes = [_vp, C.c_int]
     L.b3d_get_correspondences.argtypes = [_vp, _vp]
     L.b3d_set_correspondences.argtypes = [_vp, _vp, C.c_int]
     L.b3d_correspondences_devptr.argtypes = [_vp, C.POINTER(_vp)]
@@ -211,6 +212,10 @@ class Context:
 
     def set_features_device(self, sd_ptr: int, td_ptr: int):
         self._check(self._L.b3d_set_features(self._h, _vp(sd_ptr), _vp(td_ptr), 1))
+
+    def set_match_mode(self, mode: int):
+        """0 auto, 1 exact CUDA-core kernel, 2 tcgen05 screen + exact re-score (identical results)."""
+        self._check(self._L.b3d_set_match_mode(self._h, mode))
 
     def match_features(self, row0=0, row1=None):
         self._check(self._L.b3d_match_features(self._h, row0, self._n_src if row1 is None else row1))

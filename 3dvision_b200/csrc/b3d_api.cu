@@ -108,7 +108,8 @@ void b3d_ctx_destroy(b3d_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     DevBuf* bufs[] = {&c->stage_a, &c->stage_b, &c->stage_c, &c->src4, &c->tgt4, &c->nrm4, &c->sdesc, &c->tdesc, &c->corr, &c->raw,
                       &c->draws, &c->scan_tmp, &c->hyp, &c->counts, &c->pairs, &c->seqsum, &c->grid_slots, &c->grid_cursor,
-                      &c->grid_pts, &c->grid_nrm, &c->pt_slot, &c->pt_rank, &c->partials, &c->nn_idx, &c->nn_d2, &c->state};
+                      &c->grid_pts, &c->grid_nrm, &c->pt_slot, &c->pt_rank, &c->partials, &c->nn_idx, &c->nn_d2, &c->state,
+                      &c->tc_a_tiles, &c->tc_b_tiles, &c->tc_norm2, &c->tc_best, &c->tc_aux};
     for (DevBuf* b : bufs) b->release();
     if (c->h_state) cudaFreeHost(c->h_state);
     for (int s = 0; s < kStages; ++s) { if (c->ev_start[s]) cudaEventDestroy(c->ev_start[s]); if (c->ev_stop[s]) cudaEventDestroy(c->ev_stop[s]); }
@@ -189,6 +190,12 @@ int b3d_set_features(b3d_ctx* c, const float* src_desc, const float* tgt_desc, i
         c->sdesc_p = c->sdesc.as<float>(); c->tdesc_p = c->tdesc.as<float>();
     }
     c->have_feats = true;
+    return B3D_OK;
+}
+
+int b3d_set_match_mode(b3d_ctx* c, int mode) {
+    if (!c || mode < 0 || mode > 2) return B3D_ERR_INVALID;
+    c->match_mode = mode;
     return B3D_OK;
 }
 

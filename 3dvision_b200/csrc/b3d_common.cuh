@@ -66,6 +66,8 @@ struct b3d_ctx {
     const float* sdesc_p = nullptr;          // where the descriptors actually live (may be caller's device memory)
     const float* tdesc_p = nullptr;
     b3d::DevBuf corr;                        // uint32 [n_src]
+    int match_mode = 0;                      // 0 auto, 1 exact CUDA-core kernel, 2 tcgen05 screen + exact re-score
+    b3d::DevBuf tc_a_tiles, tc_b_tiles, tc_norm2, tc_best, tc_aux;
 
     // RANSAC
     std::mt19937 host_rng{42};               // src/registration.cpp:235 — seed is the literal 42
@@ -127,6 +129,7 @@ struct StageTimer {
 
 // stages implemented in the .cu files
 int match_features_impl(b3d_ctx* c, size_t row0, size_t row1);
+int match_features_tc_impl(b3d_ctx* c, size_t row0, size_t row1);
 int ransac_prepare_impl(b3d_ctx* c, float voxel, int max_iterations, float confidence);
 int ransac_score_impl(b3d_ctx* c, int h0, int h1);
 int ransac_reduce_impl(b3d_ctx* c, int h0, int h1, const int64_t* limit_key_dev, int64_t* keys_dev);

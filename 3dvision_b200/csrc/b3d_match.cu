@@ -102,6 +102,9 @@ int match_features_impl(b3d_ctx* c, size_t row0, size_t row1) {
         B3D_CUDA(c, cudaMemsetAsync(c->corr.as<uint32_t>() + row0, 0, sizeof(uint32_t) * (row1 - row0), c->stream));
         return B3D_OK;
     }
+    // tensor-core screen pays off once there are enough pairs to amortise operand packing
+    const bool use_tc = c->match_mode == 2 || (c->match_mode == 0 && (double)(row1 - row0) * (double)c->n_tgt >= 2.5e7);
+    if (use_tc) return match_features_tc_impl(c, row0, row1);
     int blocks = div_up((long long)(row1 - row0), kMT);
     match_exact_kernel<<<blocks, kMatchThreads, 0, c->stream>>>(c->sdesc_p, c->tdesc_p, (unsigned)row0, (unsigned)row1,
                                                                 (unsigned)c->n_tgt, c->corr.as<uint32_t>());

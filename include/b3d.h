@@ -105,6 +105,9 @@ int b3d_set_clouds(b3d_ctx* ctx, const float* src_xyz, size_t n_src,
                    const float* tgt_xyz, const float* tgt_normals_or_null, size_t n_tgt, int on_device);
 int b3d_set_features(b3d_ctx* ctx, const float* src_desc, const float* tgt_desc, int on_device);
 
+/* Kernel used by descriptor matching: 0 = automatic, 1 = exact CUDA-core brute force,
+ * 2 = tcgen05 tensor-core screen + exact fp32 re-score. All three return identical indices. */
+int b3d_set_match_mode(b3d_ctx* ctx, int mode);
 /* src/registration.cpp:216-232 for source rows [row0,row1). */
 int b3d_match_features(b3d_ctx* ctx, size_t row0, size_t row1);
 int b3d_get_correspondences(b3d_ctx* ctx, uint32_t* out_host /* [n_src] */);
