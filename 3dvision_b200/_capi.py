@@ -28,9 +28,9 @@ SYMBOLS = [
     "b3d_cuda_available", "b3d_ctx_create", "b3d_ctx_destroy", "b3d_ctx_set_stream", "b3d_strerror", "b3d_last_error",
     "b3d_ransac", "b3d_icp",
     "b3d_set_clouds", "b3d_set_features", "b3d_set_match_mode", "b3d_match_features", "b3d_get_correspondences", "b3d_set_correspondences",
-    "b3d_correspondences_devptr", "b3d_ransac_prepare", "b3d_ransac_score", "b3d_ransac_reduce", "b3d_ransac_finish",
+    "b3d_correspondences_devptr", "b3d_set_score_mode", "b3d_ransac_prepare", "b3d_ransac_score", "b3d_ransac_reduce", "b3d_ransac_finish",
     "b3d_ransac_counts", "b3d_ransac_hypotheses", "b3d_icp_run", "b3d_icp_nearest",
-    "b3d_kernel_launches", "b3d_stage_ms", "b3d_measure_fp32_rate",
+    "b3d_kernel_launches", "b3d_stage_ms", "b3d_measure_fp32_rate", "b3d_score_recounts",
 ]
 
 
@@ -79,6 +79,7 @@ def _declare(L):
     L.b3d_set_features.argtypes = [_vp, _vp, _vp, C.c_int]
     L.b3d_match_features.argtypes = [_vp, C.c_size_t, C.c_size_t]
     L.b3d_set_match_mode.argtypes = [_vp, C.c_int]
+    L.b3d_set_score_mode.argtypes = [_vp, C.c_int]
     L.b3d_get_correspondences.argtypes = [_vp, _vp]
     L.b3d_set_correspondences.argtypes = [_vp, _vp, C.c_int]
     L.b3d_correspondences_devptr.argtypes = [_vp, C.POINTER(_vp)]
@@ -95,6 +96,7 @@ def _declare(L):
     L.b3d_stage_ms.argtypes = [_vp, C.c_int]
     L.b3d_stage_ms.restype = C.c_float
     L.b3d_measure_fp32_rate.argtypes = [_vp, C.POINTER(C.c_double)]
+    L.b3d_score_recounts.argtypes = [_vp, C.POINTER(C.c_uint64)]
 
 
 def cuda_available() -> bool:
@@ -161,6 +163,11 @@ class Context:
 
     def stage_ms(self, stage: int) -> float:
         return float(self._L.b3d_stage_ms(self._h, stage))
+
+    def score_recounts(self) -> int:
+        v = C.c_uint64()
+        self._check(self._L.b3d_score_recounts(self._h, C.byref(v)))
+        return int(v.value)
 
     def measure_fp32_rate(self) -> float:
         """Sustained un-fused FMUL+FADD lane-ops/s on this device (scoring-kernel roofline)."""
@@ -239,6 +246,10 @@ class Context:
         p = _vp()
         self._check(self._L.b3d_correspondences_devptr(self._h, C.byref(p)))
         return int(p.value)
+
+    def set_score_mode(self, mode: int):
+        """0 FMA screen + exact band re-count (default), 1 un-fused arithmetic everywhere (identical counts)."""
+        self._check(self._L.b3d_set_score_mode(self._h, mode))
 
     def ransac_prepare(self, voxel_size, max_iterations, confidence):
         self._H = max_iterations

@@ -199,6 +199,22 @@ int b3d_set_match_mode(b3d_ctx* c, int mode) {
     return B3D_OK;
 }
 
+int b3d_score_recounts(b3d_ctx* c, uint64_t* out) {
+    if (!c || !out) return B3D_ERR_INVALID;
+    B3D_CUDA(c, cudaSetDevice(c->device));
+    unsigned long long v = 0;
+    B3D_CUDA(c, cudaMemcpyAsync(&v, &c->state.as<DeviceState>()->score_recounts, sizeof(v), cudaMemcpyDeviceToHost, c->stream));
+    B3D_CUDA(c, cudaStreamSynchronize(c->stream));
+    *out = v;
+    return B3D_OK;
+}
+
+int b3d_set_score_mode(b3d_ctx* c, int mode) {
+    if (!c || mode < 0 || mode > 2) return B3D_ERR_INVALID;
+    c->score_mode = mode;
+    return B3D_OK;
+}
+
 int b3d_match_features(b3d_ctx* c, size_t row0, size_t row1) {
     if (!c) return B3D_ERR_INVALID;
     B3D_CUDA(c, cudaSetDevice(c->device));

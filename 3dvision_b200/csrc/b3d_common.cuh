@@ -38,6 +38,9 @@ struct DeviceState {
     unsigned long long exit_key;      // 0xFFFFFFFF - first id with fitness > confidence; 0 = none
     unsigned int accepted_total;      // accepted RNG draws inside the raw window
     unsigned int pad0;
+    unsigned int pair_smax_bits;      // max |coordinate| over source / matched-target points of the pair array
+    unsigned int pair_qmax_bits;
+    unsigned long long score_recounts; // 32-pair groups re-counted with the reference arithmetic by the last score call
     // ICP
     float T[16];                      // current transform, column-major
     float res_T[16];                  // RegistrationResult.transformation
@@ -80,6 +83,8 @@ struct b3d_ctx {
     b3d::DevBuf pairs;                       // float4 [2][n_src]: (s_i, 0), (q_corr[i], 0)
     b3d::DevBuf seqsum;                      // float scratch for the exact sequential rmse sum
     int H = 0;
+    unsigned pair_stride = 0;                // pair array stride (n_src rounded up to the pair tile)
+    int score_mode = 0;                      // 0 = FMA screen + exact band re-count, 1 = un-fused arithmetic everywhere
     float ransac_thr = 0.f, ransac_cut = 0.f, confidence = 0.f;
     bool prepared = false, scored = false;
     int scored_lo = 0, scored_hi = 0;

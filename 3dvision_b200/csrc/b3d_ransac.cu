@@ -43,14 +43,34 @@ struct DrawEmit {
 };
 
 // ---------------------------------------------------------------------------------
-// pairs[i] = s_i ; pairs[n + i] = q_{corr[i]}
+// pairs[i] = s_i ; pairs[stride + i] = q_{corr[i]}.  stride = n rounded up to the pair tile; the
+// padding holds sentinel pairs that can never be inliers.  Also records max |coordinate| of
+// both sides (float bits, atomicMax) for the screening error bound.
 // ---------------------------------------------------------------------------------
 __global__ void gather_pairs_kernel(const float4* __restrict__ src4, const float4* __restrict__ tgt4,
-                                    const uint32_t* __restrict__ corr, unsigned n, unsigned n_tgt, float4* __restrict__ pairs) {
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        pairs[i] = src4[i];
-        unsigned j = corr[i];
-        pairs[n + i] = (j < n_tgt) ? tgt4[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+                                    const uint32_t* __restrict__ corr, unsigned n, unsigned n_tgt, unsigned stride,
+                                    float4* __restrict__ pairs, DeviceState* __restrict__ st) {
+    float smax = 0.0f, qmax = 0.0f;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < stride; i += gridDim.x * blockDim.x) {
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = make_float4(1e18f, 1e18f, 1e18f, 0.f);
+        if (i < n) {
+            s = src4[i];
+            unsigned j = corr[i];
+            q = (j < n_tgt) ? tgt4[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+            smax = fmaxf(smax, fmaxf(fabsf(s.x), fmaxf(fabsf(s.y), fabsf(s.z))));
+            qmax = fmaxf(qmax, fmaxf(fabsf(q.x), fmaxf(fabsf(q.y), fabsf(q.z))));
+        }
+        pairs[i] = s;
+        pairs[stride + i] = q;
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+        smax = fmaxf(smax, __shfl_xor_sync(0xffffffffu, smax, m));
+        qmax = fmaxf(qmax, __shfl_xor_sync(0xffffffffu, qmax, m));
+    }
+    if ((threadIdx.x & 31) == 0) {      // NaN-free by construction of fmaxf; inf stays inf and disables the screen
+        atomicMax(&st->pair_smax_bits, __float_as_uint(smax));
+        atomicMax(&st->pair_qmax_bits, __float_as_uint(qmax));
     }
 }
 
@@ -58,7 +78,7 @@ __global__ void gather_pairs_kernel(const float4* __restrict__ src4, const float
 // hypothesis generation: hyp is SoA float[12][H]
 // ---------------------------------------------------------------------------------
 __global__ void hypothesis_kernel(const uint32_t* __restrict__ draws, const DeviceState* __restrict__ st,
-                                  const float4* __restrict__ pairs, unsigned n_src, int H,
+                                  const float4* __restrict__ pairs, unsigned pair_stride, int H,
                                   float* __restrict__ hyp, int* __restrict__ counts) {
     int h = blockIdx.x * blockDim.x + threadIdx.x;
     if (h >= H) return;
@@ -74,7 +94,7 @@ __global__ void hypothesis_kernel(const uint32_t* __restrict__ draws, const Devi
     const uint32_t id[3] = {i0, i1, i2};
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        float4 a = pairs[id[k]], b = pairs[n_src + id[k]];
+        float4 a = pairs[id[k]], b = pairs[pair_stride + id[k]];
         s[k][0] = a.x; s[k][1] = a.y; s[k][2] = a.z;
         q[k][0] = b.x; q[k][1] = b.y; q[k][2] = b.z;
     }
@@ -103,7 +123,7 @@ constexpr int kPairTile = 512;        // pairs per smem tile: 2 x 8 KB
 template <int KH>
 __global__ void __launch_bounds__(kScoreThreads)
 score_exact_kernel(const float* __restrict__ hyp, int H, int h0, int h1,
-                   const float4* __restrict__ pairs, unsigned n_pairs, unsigned pairs_per_y,
+                   const float4* __restrict__ pairs, unsigned n_pairs, unsigned pair_stride, unsigned pairs_per_y,
                    float cut, int* __restrict__ counts) {
     __shared__ float4 sS[kPairTile];
     __shared__ float4 sQ[kPairTile];
@@ -126,7 +146,7 @@ score_exact_kernel(const float* __restrict__ hyp, int H, int h0, int h1,
     for (unsigned base = p_begin; base < p_end; base += kPairTile) {
         const unsigned m = min((unsigned)kPairTile, p_end - base);
         __syncthreads();
-        for (unsigned e = tid; e < m; e += kScoreThreads) { sS[e] = pairs[base + e]; sQ[e] = pairs[n_pairs + base + e]; }
+        for (unsigned e = tid; e < m; e += kScoreThreads) { sS[e] = pairs[base + e]; sQ[e] = pairs[pair_stride + base + e]; }
         __syncthreads();
 #pragma unroll 4
         for (unsigned j = 0; j < m; ++j) {
@@ -151,6 +171,260 @@ score_exact_kernel(const float* __restrict__ hyp, int H, int h0, int h1,
             else if (cnt[k]) atomicAdd(&counts[h], cnt[k]);
         }
     }
+}
+
+// Screened scoring.  The reference's un-fused arithmetic costs 27 instructions per
+// (hypothesis, pair); the same squared distance evaluated with FMAs costs 15.  The two values
+// differ by at most `beta` (derived in DESIGN.md from the 11 roundings per coordinate), so
+//   d2_fma <  cut - beta  => the reference counts the pair,
+//   d2_fma >  cut + beta  => it does not,
+// and only pairs inside the band need the reference arithmetic.  Each thread keeps two counters
+// per hypothesis over a group of 32 pairs (below lo / below hi); when they agree the group had no
+// pair in the band and the count is exact by construction, otherwise that group alone is
+// re-counted with the un-fused arithmetic, cooperatively by the whole warp.  The inner loop stays
+// branch-free.
+constexpr int kGroup = 32;
+
+// One compare + one predicated add each (the compiler otherwise emits add-then-conditional-move
+// pairs; ALU-pipe instructions cost two issue cycles on this part, so they are worth trimming).
+__device__ __forceinline__ void count_below(int& cnt, float v, float bound) {       // cnt += (v < bound)
+    asm("{\n\t.reg .pred p;\n\tsetp.lt.f32 p, %1, %2;\n\t@p add.s32 %0, %0, 1;\n\t}" : "+r"(cnt) : "f"(v), "f"(bound));
+}
+__device__ __forceinline__ void count_not_above(int& cnt, float v, float bound) {   // cnt += !(v > bound); NaN counts
+    asm("{\n\t.reg .pred p;\n\tsetp.gt.f32 p, %1, %2;\n\t@!p add.s32 %0, %0, 1;\n\t}" : "+r"(cnt) : "f"(v), "f"(bound));
+}
+
+// Warp-cooperative exact re-count of one 32-pair group for the hypothesis held by `src_lane`:
+// (R,t) is broadcast with shuffles, lane l evaluates pair l with the reference arithmetic, and
+// the count is a ballot.  ~45 warp instructions instead of 32 x 27 serial ones in one lane.
+__device__ __forceinline__ int warp_exact_group_count(const float (&R)[9], const float (&t)[3], int src_lane,
+                                                      const float4* sS, const float4* sQ, float cut) {
+    float Rb[9], tb[3];
+#pragma unroll
+    for (int e = 0; e < 9; ++e) Rb[e] = __shfl_sync(0xffffffffu, R[e], src_lane);
+#pragma unroll
+    for (int e = 0; e < 3; ++e) tb[e] = __shfl_sync(0xffffffffu, t[e], src_lane);
+    const int lane = threadIdx.x & 31;
+    const float4 s = sS[lane], q = sQ[lane];
+    float x = (Rb[0] * s.x + (Rb[1] * s.y + Rb[2] * s.z)) + tb[0];
+    float y = (Rb[3] * s.x + (Rb[4] * s.y + Rb[5] * s.z)) + tb[1];
+    float z = (Rb[6] * s.x + (Rb[7] * s.y + Rb[8] * s.z)) + tb[2];
+    float dx = x - q.x, dy = y - q.y, dz = z - q.z;
+    float d2 = dx * dx + (dy * dy + dz * dz);
+    return __popc(__ballot_sync(0xffffffffu, d2 < cut));
+}
+
+template <int KH>
+__global__ void __launch_bounds__(kScoreThreads)
+score_screen_kernel(const float* __restrict__ hyp, int H, int h0, int h1,
+                    const float4* __restrict__ pairs, unsigned pair_stride, unsigned pairs_per_y,
+                    float cut, float thr, const DeviceState* __restrict__ st, int* __restrict__ counts) {
+    __shared__ float4 sS[kPairTile];
+    __shared__ float4 sQ[kPairTile];
+    const int tid = threadIdx.x;
+    float R[KH][9], t[KH][3], lo[KH], hi[KH];
+    int total[KH], hid[KH];
+    unsigned recounts = 0;
+    const float smax = __uint_as_float(st->pair_smax_bits), qmax = __uint_as_float(st->pair_qmax_bits);
+#pragma unroll
+    for (int k = 0; k < KH; ++k) {
+        int h = h0 + (blockIdx.x * KH + k) * kScoreThreads + tid;
+        hid[k] = h;
+        int hc = h < h1 ? h : h1 - 1;
+#pragma unroll
+        for (int e = 0; e < 9; ++e) R[k][e] = hyp[(size_t)e * H + hc];
+#pragma unroll
+        for (int e = 0; e < 3; ++e) t[k][e] = hyp[(size_t)(9 + e) * H + hc];
+        total[k] = 0;
+        // error bound of the fused evaluation against the reference's (see header comment)
+        float rowsum = fmaxf(fabsf(R[k][0]) + fabsf(R[k][1]) + fabsf(R[k][2]),
+                             fmaxf(fabsf(R[k][3]) + fabsf(R[k][4]) + fabsf(R[k][5]), fabsf(R[k][6]) + fabsf(R[k][7]) + fabsf(R[k][8])));
+        float A = rowsum * smax + fmaxf(fabsf(t[k][0]), fmaxf(fabsf(t[k][1]), fabsf(t[k][2]))) + qmax;
+        float e = A * 7.152557373046875e-7f;                    // 12 * 2^-24 * A  (11 roundings per coordinate + margin)
+        float beta = 4.0f * (thr * 1.02f + e) * e + 2e-6f * cut;
+        if (beta < 0.5f * cut) { lo[k] = cut - beta; hi[k] = cut + beta; }
+        else { lo[k] = -INFINITY; hi[k] = INFINITY; }           // bound useless or NaN: every group is re-counted exactly
+    }
+    const unsigned p_begin = blockIdx.y * pairs_per_y;
+    const unsigned p_end = min(pair_stride, p_begin + pairs_per_y);     // multiples of kPairTile
+    for (unsigned base = p_begin; base < p_end; base += kPairTile) {
+        __syncthreads();
+        for (unsigned e = tid; e < kPairTile; e += kScoreThreads) { sS[e] = pairs[base + e]; sQ[e] = pairs[pair_stride + base + e]; }
+        __syncthreads();
+#pragma unroll 1
+        for (int g = 0; g < kPairTile; g += kGroup) {
+            int clo[KH], chi[KH];
+#pragma unroll
+            for (int k = 0; k < KH; ++k) { clo[k] = 0; chi[k] = 0; }
+#pragma unroll 8
+            for (int j = 0; j < kGroup; ++j) {
+                const float4 s = sS[g + j], q = sQ[g + j];
+#pragma unroll
+                for (int k = 0; k < KH; ++k) {
+                    float dx = __fmaf_rn(R[k][0], s.x, __fmaf_rn(R[k][1], s.y, __fmaf_rn(R[k][2], s.z, t[k][0] - q.x)));
+                    float dy = __fmaf_rn(R[k][3], s.x, __fmaf_rn(R[k][4], s.y, __fmaf_rn(R[k][5], s.z, t[k][1] - q.y)));
+                    float dz = __fmaf_rn(R[k][6], s.x, __fmaf_rn(R[k][7], s.y, __fmaf_rn(R[k][8], s.z, t[k][2] - q.z)));
+                    float d2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx));
+                    count_below(clo[k], d2, lo[k]);
+                    count_not_above(chi[k], d2, hi[k]);         // NaN counts as "maybe"
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < KH; ++k) {
+                unsigned need = __ballot_sync(0xffffffffu, clo[k] != chi[k]);     // lanes whose group touched the band
+                while (need) {
+                    const int src = __ffs(need) - 1;
+                    need &= need - 1u;
+                    ++recounts;
+                    const int exact = warp_exact_group_count(R[k], t[k], src, sS + g, sQ + g, cut);
+                    if ((threadIdx.x & 31) == src) clo[k] = exact;
+                }
+                total[k] += clo[k];
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < KH; ++k) {
+        int h = hid[k];
+        if (h < h1 && counts[h] >= 0) {
+            if (gridDim.y == 1) counts[h] = total[k];
+            else if (total[k]) atomicAdd(&counts[h], total[k]);
+        }
+    }
+    if ((tid & 31) == 0 && recounts) atomicAdd(const_cast<unsigned long long*>(&st->score_recounts), (unsigned long long)recounts);
+}
+
+// Packed variant of the screen: Blackwell's fma.rn.f32x2 / add.rn.f32x2 / mul.rn.f32x2 (FFMA2,
+// FADD2, FMUL2) evaluate two hypotheses per instruction.  The math throughput per lane is the
+// same as scalar FFMA, but the instruction count halves, which matters because the scalar
+// kernels are bound by instruction issue (1 warp-instruction / clock / SM sub-partition), not by
+// the FMA pipe.  Pair tiles are staged in shared memory pre-duplicated ((sx,sx),(sy,sy),...) and
+// pre-negated (-q) so every operand of the packed chain is a 64-bit register pair.
+__device__ __forceinline__ unsigned long long pk2(float a, float b) {
+    unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r;
+}
+__device__ __forceinline__ void upk2(unsigned long long v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d;
+}
+__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
+    unsigned long long d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
+}
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
+    unsigned long long d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
+}
+
+__device__ __forceinline__ float screen_lo_hi(const float* R, const float* t, float smax, float qmax, float thr, float cut, float& lo, float& hi) {
+    float rowsum = fmaxf(fabsf(R[0]) + fabsf(R[1]) + fabsf(R[2]), fmaxf(fabsf(R[3]) + fabsf(R[4]) + fabsf(R[5]), fabsf(R[6]) + fabsf(R[7]) + fabsf(R[8])));
+    float A = rowsum * smax + fmaxf(fabsf(t[0]), fmaxf(fabsf(t[1]), fabsf(t[2]))) + qmax;
+    float e = A * 7.152557373046875e-7f;                        // 12 * 2^-24 * A
+    float beta = 4.0f * (thr * 1.02f + e) * e + 2e-6f * cut;
+    if (beta < 0.5f * cut) { lo = cut - beta; hi = cut + beta; } else { lo = -INFINITY; hi = INFINITY; }
+    return beta;
+}
+
+template <int KP>      // packed hypothesis pairs per thread (KH = 2 * KP hypotheses)
+__global__ void __launch_bounds__(kScoreThreads)
+score_screen2_kernel(const float* __restrict__ hyp, int H, int h0, int h1,
+                     const float4* __restrict__ pairs, unsigned pair_stride, unsigned pairs_per_y,
+                     float cut, float thr, const DeviceState* __restrict__ st, int* __restrict__ counts) {
+    constexpr int KH = 2 * KP;
+    __shared__ float4 sP0[kPairTile];      // (sx, sx, sy, sy)
+    __shared__ float4 sP1[kPairTile];      // (sz, sz, -qx, -qx)
+    __shared__ float4 sP2[kPairTile];      // (-qy, -qy, -qz, -qz)
+    const int tid = threadIdx.x, lane = tid & 31;
+    float R[KH][9], t[KH][3], lo[KH], hi[KH];
+    unsigned long long Rp[KP][9], tp[KP][3];
+    int total[KH], hid[KH];
+    unsigned recounts = 0;
+    const float smax = __uint_as_float(st->pair_smax_bits), qmax = __uint_as_float(st->pair_qmax_bits);
+#pragma unroll
+    for (int k = 0; k < KH; ++k) {
+        int h = h0 + (blockIdx.x * KH + k) * kScoreThreads + tid;
+        hid[k] = h;
+        int hc = h < h1 ? h : h1 - 1;
+#pragma unroll
+        for (int e = 0; e < 9; ++e) R[k][e] = hyp[(size_t)e * H + hc];
+#pragma unroll
+        for (int e = 0; e < 3; ++e) t[k][e] = hyp[(size_t)(9 + e) * H + hc];
+        total[k] = 0;
+        screen_lo_hi(R[k], t[k], smax, qmax, thr, cut, lo[k], hi[k]);
+    }
+#pragma unroll
+    for (int p = 0; p < KP; ++p) {
+#pragma unroll
+        for (int e = 0; e < 9; ++e) Rp[p][e] = pk2(R[2 * p][e], R[2 * p + 1][e]);
+#pragma unroll
+        for (int e = 0; e < 3; ++e) tp[p][e] = pk2(t[2 * p][e], t[2 * p + 1][e]);
+    }
+    const unsigned p_begin = blockIdx.y * pairs_per_y;
+    const unsigned p_end = min(pair_stride, p_begin + pairs_per_y);
+    for (unsigned base = p_begin; base < p_end; base += kPairTile) {
+        __syncthreads();
+        for (unsigned e = tid; e < kPairTile; e += kScoreThreads) {
+            const float4 s = pairs[base + e], q = pairs[pair_stride + base + e];
+            sP0[e] = make_float4(s.x, s.x, s.y, s.y);
+            sP1[e] = make_float4(s.z, s.z, -q.x, -q.x);
+            sP2[e] = make_float4(-q.y, -q.y, -q.z, -q.z);
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int g = 0; g < kPairTile; g += kGroup) {
+            int clo[KH], chi[KH];
+#pragma unroll
+            for (int k = 0; k < KH; ++k) { clo[k] = 0; chi[k] = 0; }
+#pragma unroll 8
+            for (int j = 0; j < kGroup; ++j) {
+                const ulonglong2 a = reinterpret_cast<const ulonglong2*>(sP0)[g + j];     // SX, SY
+                const ulonglong2 b = reinterpret_cast<const ulonglong2*>(sP1)[g + j];     // SZ, -QX
+                const ulonglong2 c = reinterpret_cast<const ulonglong2*>(sP2)[g + j];     // -QY, -QZ
+#pragma unroll
+                for (int p = 0; p < KP; ++p) {
+                    unsigned long long dx = fma2(Rp[p][0], a.x, fma2(Rp[p][1], a.y, fma2(Rp[p][2], b.x, add2(tp[p][0], b.y))));
+                    unsigned long long dy = fma2(Rp[p][3], a.x, fma2(Rp[p][4], a.y, fma2(Rp[p][5], b.x, add2(tp[p][1], c.x))));
+                    unsigned long long dz = fma2(Rp[p][6], a.x, fma2(Rp[p][7], a.y, fma2(Rp[p][8], b.x, add2(tp[p][2], c.y))));
+                    unsigned long long d2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
+                    float d2a, d2b; upk2(d2, d2a, d2b);
+                    count_below(clo[2 * p], d2a, lo[2 * p]);         count_not_above(chi[2 * p], d2a, hi[2 * p]);
+                    count_below(clo[2 * p + 1], d2b, lo[2 * p + 1]); count_not_above(chi[2 * p + 1], d2b, hi[2 * p + 1]);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < KH; ++k) {
+                unsigned need = __ballot_sync(0xffffffffu, clo[k] != chi[k]);
+                while (need) {
+                    const int src = __ffs(need) - 1;
+                    need &= need - 1u;
+                    ++recounts;
+                    // exact re-count of this 32-pair group for lane src's hypothesis k, one pair per lane
+                    float Rb[9], tb[3];
+#pragma unroll
+                    for (int e = 0; e < 9; ++e) Rb[e] = __shfl_sync(0xffffffffu, R[k][e], src);
+#pragma unroll
+                    for (int e = 0; e < 3; ++e) tb[e] = __shfl_sync(0xffffffffu, t[k][e], src);
+                    const float4 pa = sP0[g + lane], pb = sP1[g + lane], pc = sP2[g + lane];
+                    const float sx = pa.x, sy = pa.z, sz = pb.x, qx = -pb.z, qy = -pc.x, qz = -pc.z;
+                    float x = (Rb[0] * sx + (Rb[1] * sy + Rb[2] * sz)) + tb[0];
+                    float y = (Rb[3] * sx + (Rb[4] * sy + Rb[5] * sz)) + tb[1];
+                    float z = (Rb[6] * sx + (Rb[7] * sy + Rb[8] * sz)) + tb[2];
+                    float ex = x - qx, ey = y - qy, ez = z - qz;
+                    float d2 = ex * ex + (ey * ey + ez * ez);
+                    const int exact = __popc(__ballot_sync(0xffffffffu, d2 < cut));
+                    if (lane == src) clo[k] = exact;
+                }
+                total[k] += clo[k];
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < KH; ++k) {
+        int h = hid[k];
+        if (h < h1 && counts[h] >= 0) {
+            if (gridDim.y == 1) counts[h] = total[k];
+            else if (total[k]) atomicAdd(&counts[h], total[k]);
+        }
+    }
+    if (lane == 0 && recounts) atomicAdd(const_cast<unsigned long long*>(&st->score_recounts), (unsigned long long)recounts);
 }
 
 // ---------------------------------------------------------------------------------
@@ -207,7 +481,7 @@ constexpr int kFinishThreads = 1024;
 
 __global__ void __launch_bounds__(kFinishThreads)
 finish_kernel(const long long* __restrict__ key_ptr, const float* __restrict__ hyp, int H,
-              const float4* __restrict__ pairs, unsigned n_pairs,
+              const float4* __restrict__ pairs, unsigned n_pairs, unsigned pair_stride,
               float n_src_f, float thr, DeviceState* __restrict__ st) {
     __shared__ float vals[kFinishThreads];
     __shared__ unsigned warp_cnt[kFinishThreads / 32];
@@ -234,7 +508,7 @@ finish_kernel(const long long* __restrict__ key_ptr, const float* __restrict__ h
         unsigned i = base + tid;
         float e2 = 0.0f; bool in = false;
         if (i < n_pairs) {
-            float4 s = pairs[i], q = pairs[n_pairs + i];
+            float4 s = pairs[i], q = pairs[pair_stride + i];
             float x = (R[0] * s.x + (R[1] * s.y + R[2] * s.z)) + t[0];
             float y = (R[3] * s.x + (R[4] * s.y + R[5] * s.z)) + t[1];
             float z = (R[6] * s.x + (R[7] * s.y + R[8] * s.z)) + t[2];
@@ -319,7 +593,9 @@ int ransac_prepare_impl(b3d_ctx* c, float voxel, int max_iterations, float confi
     const int H = max_iterations;
     const unsigned n = (unsigned)c->n_src;
     if (H == 0 || n == 0) { c->prepared = true; return B3D_OK; }
-    B3D_CUDA(c, c->pairs.ensure(sizeof(float4) * 2 * (size_t)n));
+    const unsigned pair_stride = (unsigned)div_up(n, kPairTile) * kPairTile;
+    c->pair_stride = pair_stride;
+    B3D_CUDA(c, c->pairs.ensure(sizeof(float4) * 2 * (size_t)pair_stride));
     B3D_CUDA(c, c->draws.ensure(sizeof(uint32_t) * 3 * (size_t)H));
     B3D_CUDA(c, c->hyp.ensure(sizeof(float) * 12 * (size_t)H));
     B3D_CUDA(c, c->counts.ensure(sizeof(int) * (size_t)H));
@@ -346,11 +622,13 @@ int ransac_prepare_impl(b3d_ctx* c, float voxel, int max_iterations, float confi
         scan_emit_kernel<<<tiles, kScanThreads, 0, c->stream>>>(accept, emit, (unsigned)window, c->scan_tmp.as<unsigned>());
         B3D_LAUNCHED(c);
         if (attempt == 0) {
-            gather_pairs_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(c->src4.as<float4>(), c->tgt4.as<float4>(),
-                                                                          c->corr.as<uint32_t>(), n, (unsigned)c->n_tgt, c->pairs.as<float4>());
+            B3D_CUDA(c, cudaMemsetAsync(&st->pair_smax_bits, 0, 2 * sizeof(unsigned), c->stream));
+            gather_pairs_kernel<<<grid_for(pair_stride, 256), 256, 0, c->stream>>>(c->src4.as<float4>(), c->tgt4.as<float4>(),
+                                                                                    c->corr.as<uint32_t>(), n, (unsigned)c->n_tgt, pair_stride,
+                                                                                    c->pairs.as<float4>(), st);
             B3D_LAUNCHED(c);
         }
-        hypothesis_kernel<<<div_up(H, 128), 128, 0, c->stream>>>(c->draws.as<uint32_t>(), st, c->pairs.as<float4>(), n, H,
+        hypothesis_kernel<<<div_up(H, 128), 128, 0, c->stream>>>(c->draws.as<uint32_t>(), st, c->pairs.as<float4>(), pair_stride, H,
                                                                    c->hyp.as<float>(), c->counts.as<int>());
         B3D_LAUNCHED(c);
         // The acceptance window is sized 8 sigma above the expectation; verify it on the host only
@@ -391,12 +669,19 @@ int ransac_score_impl(b3d_ctx* c, int h0, int h1) {
         B3D_LAUNCHED(c);
     }
     dim3 grid(bx, by);
-    if (KH == 2)
-        score_exact_kernel<2><<<grid, kScoreThreads, 0, c->stream>>>(c->hyp.as<float>(), c->H, h0, h1, c->pairs.as<float4>(), n, per_y,
-                                                                     c->ransac_cut, c->counts.as<int>());
-    else
-        score_exact_kernel<1><<<grid, kScoreThreads, 0, c->stream>>>(c->hyp.as<float>(), c->H, h0, h1, c->pairs.as<float4>(), n, per_y,
-                                                                     c->ransac_cut, c->counts.as<int>());
+    B3D_CUDA(c, cudaMemsetAsync(&c->state.as<DeviceState>()->score_recounts, 0, sizeof(unsigned long long), c->stream));
+    const float4* pairs = c->pairs.as<float4>();
+    const DeviceState* st = c->state.as<DeviceState>();
+    if (c->score_mode == 1) {               // reference arithmetic for every pair (verification / comparison)
+        if (KH == 2) score_exact_kernel<2><<<grid, kScoreThreads, 0, c->stream>>>(c->hyp.as<float>(), c->H, h0, h1, pairs, n, c->pair_stride, per_y, c->ransac_cut, c->counts.as<int>());
+        else         score_exact_kernel<1><<<grid, kScoreThreads, 0, c->stream>>>(c->hyp.as<float>(), c->H, h0, h1, pairs, n, c->pair_stride, per_y, c->ransac_cut, c->counts.as<int>());
+    } else if (c->score_mode == 0) {        // packed FFMA2 screen (two hypotheses per instruction)
+        if (KH == 2) score_screen2_kernel<1><<<grid, kScoreThreads, 0, c->stream>>>(c->hyp.as<float>(), c->H, h0, h1, pairs, c->pair_stride, per_y, c->ransac_cut, c->ransac_thr, st, c->counts.as<int>());
+        else         score_screen_kernel<1><<<grid, kScoreThreads, 0, c->stream>>>(c->hyp.as<float>(), c->H, h0, h1, pairs, c->pair_stride, per_y, c->ransac_cut, c->ransac_thr, st, c->counts.as<int>());
+    } else {                                // scalar FMA screen
+        if (KH == 2) score_screen_kernel<2><<<grid, kScoreThreads, 0, c->stream>>>(c->hyp.as<float>(), c->H, h0, h1, pairs, c->pair_stride, per_y, c->ransac_cut, c->ransac_thr, st, c->counts.as<int>());
+        else         score_screen_kernel<1><<<grid, kScoreThreads, 0, c->stream>>>(c->hyp.as<float>(), c->H, h0, h1, pairs, c->pair_stride, per_y, c->ransac_cut, c->ransac_thr, st, c->counts.as<int>());
+    }
     B3D_LAUNCHED(c);
     return B3D_OK;
 }
@@ -439,7 +724,7 @@ int ransac_finish_impl(b3d_ctx* c, const int64_t* keys_dev, float* T, float* fit
     {
         StageTimer timer(c, 3);
         finish_kernel<<<1, kFinishThreads, 0, c->stream>>>(reinterpret_cast<const long long*>(keys_dev), c->hyp.as<float>(), c->H,
-                                                           c->pairs.as<float4>(), (unsigned)c->n_src,
+                                                           c->pairs.as<float4>(), (unsigned)c->n_src, c->pair_stride,
                                                            (float)c->n_src, c->ransac_thr, st);
         B3D_LAUNCHED(c);
     }

@@ -118,6 +118,9 @@ int b3d_correspondences_devptr(b3d_ctx* ctx, void** out_devptr);
 /* src/registration.cpp:213, 235-268: threshold, RNG stream -> index triples,
  * 3-point Kabsch (R,t) for hypotheses [0,max_iterations). */
 int b3d_ransac_prepare(b3d_ctx* ctx, float voxel_size, int max_iterations, float confidence);
+/* Inlier-scoring kernel: 0 = FMA screen with exact re-count of pairs inside the error band
+ * (default), 1 = the reference's un-fused arithmetic for every pair. Identical counts. */
+int b3d_set_score_mode(b3d_ctx* ctx, int mode);
 /* src/registration.cpp:270-279 for hypothesis ids [h0,h1) (this rank's shard). */
 int b3d_ransac_score(b3d_ctx* ctx, int h0, int h1);
 /* src/registration.cpp:281-290 over ids [h0,h1): writes two int64 keys to keys_dev
@@ -151,6 +154,10 @@ uint64_t b3d_kernel_launches(const b3d_ctx* ctx);
  * context's stream: 0 match, 1 ransac_prepare, 2 ransac_score, 3 ransac_reduce+finish,
  * 4 icp grid build, 5 icp iterations. Returns -1 for an unknown stage. */
 float b3d_stage_ms(const b3d_ctx* ctx, int stage);
+
+/* Number of 32-pair groups the last b3d_ransac_score call had to re-count with the reference
+ * arithmetic because a pair fell inside the screening error band (diagnostic). */
+int b3d_score_recounts(b3d_ctx* ctx, uint64_t* out_groups);
 
 /* Measures the sustained issue rate of separate (un-fused) FMUL + FADD instructions on this
  * device, in lane-operations per second: the roofline denominator of the scoring kernel, whose
