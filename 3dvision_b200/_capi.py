@@ -27,7 +27,7 @@ NO_MATCH = 0xFFFFFFFF
 SYMBOLS = [
     "b3d_cuda_available", "b3d_ctx_create", "b3d_ctx_destroy", "b3d_ctx_set_stream", "b3d_strerror", "b3d_last_error",
     "b3d_ransac", "b3d_icp",
-    "b3d_set_clouds", "b3d_set_features", "b3d_set_match_mode", "b3d_match_features", "b3d_get_correspondences", "b3d_set_correspondences",
+    "b3d_set_clouds", "b3d_set_features", "b3d_set_match_mode", "b3d_match_features", "b3d_get_correspondences", "b3d_get_correspondences_dev", "b3d_set_correspondences",
     "b3d_correspondences_devptr", "b3d_set_score_mode", "b3d_ransac_prepare", "b3d_ransac_score", "b3d_ransac_reduce", "b3d_ransac_finish",
     "b3d_ransac_counts", "b3d_ransac_hypotheses", "b3d_icp_run", "b3d_icp_nearest",
     "b3d_kernel_launches", "b3d_stage_ms", "b3d_measure_fp32_rate", "b3d_score_recounts",
@@ -82,6 +82,7 @@ def _declare(L):
     L.b3d_set_score_mode.argtypes = [_vp, C.c_int]
     L.b3d_get_correspondences.argtypes = [_vp, _vp]
     L.b3d_set_correspondences.argtypes = [_vp, _vp, C.c_int]
+    L.b3d_get_correspondences_dev.argtypes = [_vp, _vp]
     L.b3d_correspondences_devptr.argtypes = [_vp, C.POINTER(_vp)]
     L.b3d_ransac_prepare.argtypes = [_vp, C.c_float, C.c_int, C.c_float]
     L.b3d_ransac_score.argtypes = [_vp, C.c_int, C.c_int]
@@ -237,6 +238,13 @@ class Context:
         if corr.shape[0] != self._n_src:
             raise ValueError("correspondences must have one entry per source point")
         self._check(self._L.b3d_set_correspondences(self._h, _ptr(corr), 0))
+
+    def get_correspondences_device(self, dst_devptr: int):
+        """Stream-ordered D2D copy of correspondences[n_src] (uint32) into caller-owned device memory."""
+        self._check(self._L.b3d_get_correspondences_dev(self._h, _vp(dst_devptr)))
+
+    def set_correspondences_device(self, src_devptr: int):
+        self._check(self._L.b3d_set_correspondences(self._h, _vp(src_devptr), 1))
 
     def mark_correspondences_set(self):
         """After writing into correspondences_devptr() directly (all-gather between ranks)."""

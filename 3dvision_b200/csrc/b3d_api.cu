@@ -232,6 +232,14 @@ int b3d_get_correspondences(b3d_ctx* c, uint32_t* out_host) {
     return B3D_OK;
 }
 
+int b3d_get_correspondences_dev(b3d_ctx* c, uint32_t* out_dev) {
+    if (!c || !out_dev) return B3D_ERR_INVALID;
+    if (!c->have_clouds || c->corr.cap < sizeof(uint32_t) * c->n_src) return fail(c, B3D_ERR_STATE, "get_correspondences_dev: none computed");
+    B3D_CUDA(c, cudaSetDevice(c->device));
+    if (c->n_src) B3D_CUDA(c, cudaMemcpyAsync(out_dev, c->corr.p, sizeof(uint32_t) * c->n_src, cudaMemcpyDeviceToDevice, c->stream));
+    return B3D_OK;
+}
+
 int b3d_set_correspondences(b3d_ctx* c, const uint32_t* corr, int on_device) {
     if (!c) return B3D_ERR_INVALID;
     if (!c->have_clouds) return fail(c, B3D_ERR_STATE, "set_correspondences: call set_clouds first");

@@ -44,11 +44,6 @@ def pack_exit_key(hyp_id: int) -> int:
     return 0xFFFFFFFF - int(hyp_id)
 
 
-class _DevArray:
-    def __init__(self, ptr: int, n: int, typestr: str):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
-
-
 class CudaBackend:
     """Adapter from a b3d Context (clouds + features already resident) to the protocol."""
 
@@ -57,15 +52,17 @@ class CudaBackend:
         self.n_src = n_src
         self.keys = torch.zeros(2, dtype=torch.int64, device="cuda")
         ctx.set_stream(torch.cuda.current_stream().cuda_stream)
-        self._corr = torch.as_tensor(_DevArray(ctx.correspondences_devptr(), max(n_src, 1), "<i4"), device="cuda")
+        self._corr = torch.zeros(max(n_src, 1), dtype=torch.int32, device="cuda")     # exchange buffer (uint32 bits)
 
     def match_rows(self, r0, r1):
-        self._corr.zero_()
         self.ctx.match_features(r0, r1)
+        self.ctx.get_correspondences_device(self._corr.data_ptr())                    # stream-ordered D2D
+        self._corr[:r0].zero_()
+        self._corr[r1:].zero_()
         return self._corr
 
     def correspondences_ready(self):
-        self.ctx.mark_correspondences_set()
+        self.ctx.set_correspondences_device(self._corr.data_ptr())
 
     def prepare(self, voxel, H, confidence):
         self.ctx.ransac_prepare(voxel, H, confidence)

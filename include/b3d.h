@@ -111,6 +111,9 @@ int b3d_set_match_mode(b3d_ctx* ctx, int mode);
 /* src/registration.cpp:216-232 for source rows [row0,row1). */
 int b3d_match_features(b3d_ctx* ctx, size_t row0, size_t row1);
 int b3d_get_correspondences(b3d_ctx* ctx, uint32_t* out_host /* [n_src] */);
+/* Stream-ordered device-to-device copy of correspondences[n_src] into caller-owned device memory
+ * (e.g. a torch tensor that is then all-reduced between ranks). */
+int b3d_get_correspondences_dev(b3d_ctx* ctx, uint32_t* out_dev /* [n_src] */);
 int b3d_set_correspondences(b3d_ctx* ctx, const uint32_t* corr /* [n_src] */, int on_device);
 /* Device pointer to correspondences[n_src] (uint32), for an all-gather between ranks. */
 int b3d_correspondences_devptr(b3d_ctx* ctx, void** out_devptr);
