@@ -1,0 +1,101 @@
+// b3d_registration_shim.hpp — C++ drop-in for the registration hot path of stojicnnnn/3DVision.
+//
+// Include this AFTER the reference's own headers (include/registration.hpp,
+// include/gpu_registration.hpp); it only needs their types:
+//   industry_picking::PointCloud          (registration.hpp:10-19)   three std::vector<Eigen::Vector3f>
+//   industry_picking::FPFHFeatures        (registration.hpp:21-24)   std::vector<std::array<float,33>>
+//   industry_picking::RegistrationResult  (registration.hpp:26-30)   Matrix4f + fitness + rmse
+// and provides, in namespace industry_picking::b3d_shim, functions with exactly the signatures of
+//   Registration::ransacRegistration      (registration.hpp:40-48)
+//   Registration::icpRefine               (registration.hpp:50-57)
+//   GPURegistration::icpRefine            (gpu_registration.hpp:10-16)
+//   GPURegistration::isCudaAvailable      (gpu_registration.hpp:18)
+// implemented over the C-ABI of b3d.h (libb3d.so, sm_100a CUDA kernels).  b3d_registration_impl.cpp
+// turns them into the out-of-line definitions of the reference's static member functions.
+//
+// Contract kept from the reference:
+//   * inputs are const& to caller-owned host memory, result by value, no state visible to the caller;
+//   * any failure (no CUDA device, CUDA error) throws std::runtime_error, so the orchestrator's
+//     catch(...) / catch(std::exception) blocks (src/pipeline.cpp:114-121, 146-149) keep working;
+//   * callable concurrently from the orchestrator's pool threads (src/pipeline.cpp:321-327): each
+//     host thread gets its own b3d_ctx (stream + workspace) through a thread_local.
+// Raw pointers are valid because std::vector<Eigen::Vector3f> is float[3n] and
+// std::vector<std::array<float,33>> is float[33n] in memory (static_asserts below).
+#pragma once
+
+#include <array>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "b3d.h"
+
+namespace industry_picking {
+namespace b3d_shim {
+
+static_assert(sizeof(Eigen::Vector3f) == 3 * sizeof(float), "Eigen::Vector3f must be 3 packed floats");
+static_assert(sizeof(std::array<float, B3D_DESC_DIM>) == B3D_DESC_DIM * sizeof(float), "descriptor rows must be 33 packed floats");
+static_assert(sizeof(Eigen::Matrix4f) == 16 * sizeof(float), "Eigen::Matrix4f must be 16 floats (column-major)");
+
+inline int& device_index() { static int dev = 0; return dev; }
+
+struct ThreadContext {
+    b3d_ctx* ctx = nullptr;
+    ~ThreadContext() { if (ctx) b3d_ctx_destroy(ctx); }
+};
+
+inline b3d_ctx* context() {
+    thread_local ThreadContext tc;
+    if (!tc.ctx) {
+        int rc = b3d_ctx_create(device_index(), &tc.ctx);
+        if (rc != B3D_OK) throw std::runtime_error(std::string("b3d: ") + b3d_strerror(rc));
+    }
+    return tc.ctx;
+}
+
+inline void check(b3d_ctx* ctx, int rc) {
+    if (rc != B3D_OK) {
+        std::string msg = b3d_last_error(ctx);
+        throw std::runtime_error("b3d: " + (msg.empty() ? std::string(b3d_strerror(rc)) : msg));
+    }
+}
+
+inline const float* xyz(const std::vector<Eigen::Vector3f>& v) { return v.empty() ? nullptr : reinterpret_cast<const float*>(v.data()); }
+
+inline RegistrationResult ransacRegistration(const PointCloud& source, const PointCloud& target,
+                                             const FPFHFeatures& source_features, const FPFHFeatures& target_features,
+                                             float voxel_size, int max_iterations = 100000, float confidence = 0.999f) {
+    if (source_features.descriptors.size() != source.points.size() || target_features.descriptors.size() != target.points.size())
+        throw std::runtime_error("b3d: descriptor count does not match point count");
+    b3d_ctx* ctx = context();
+    RegistrationResult result;
+    const float* sd = source_features.descriptors.empty() ? nullptr : source_features.descriptors.data()->data();
+    const float* td = target_features.descriptors.empty() ? nullptr : target_features.descriptors.data()->data();
+    check(ctx, b3d_ransac(ctx, xyz(source.points), source.points.size(), xyz(target.points), target.points.size(), sd, td,
+                          voxel_size, max_iterations, confidence, result.transformation.data(), &result.fitness, &result.rmse, nullptr));
+    return result;
+}
+
+inline RegistrationResult icpRefine(const PointCloud& source, const PointCloud& target, const Eigen::Matrix4f& initial_transform,
+                                    float distance_threshold, int max_iterations = 200, bool point_to_plane = true) {
+    b3d_ctx* ctx = context();
+    RegistrationResult result;
+    const bool has_normals = target.normals.size() == target.points.size() && !target.points.empty();   // PointCloud::hasNormals()
+    check(ctx, b3d_icp(ctx, xyz(source.points), source.points.size(), xyz(target.points), has_normals ? xyz(target.normals) : nullptr,
+                       target.points.size(), initial_transform.data(), distance_threshold, max_iterations, point_to_plane ? 1 : 0,
+                       result.transformation.data(), &result.fitness, &result.rmse, nullptr));
+    return result;
+}
+
+inline bool isCudaAvailable() { return b3d_cuda_available() != 0; }
+
+// GPURegistration::icpRefine has no point_to_plane argument; the reference GPU path is always
+// point-to-plane (src/gpu_impl.cpp:141-260).  Parity target is the CPU semantics.
+inline RegistrationResult gpuIcpRefine(const PointCloud& source, const PointCloud& target, const Eigen::Matrix4f& initial_transform,
+                                       float distance_threshold, int max_iterations = 200) {
+    if (!isCudaAvailable()) throw std::runtime_error("CUDA not available");      // src/gpu_impl.cpp:258
+    return icpRefine(source, target, initial_transform, distance_threshold, max_iterations, true);
+}
+
+}  // namespace b3d_shim
+}  // namespace industry_picking
