@@ -13,7 +13,7 @@ namespace b3d {
 
 constexpr int kNumSMs = 148;          // B200: 2 dies x 74 SMs; grids are sized in multiples of this
 constexpr int kDescDim = B3D_DESC_DIM;
-constexpr int kStages = 6;
+constexpr int kStages = 7;
 
 struct DevBuf {
     void* p = nullptr;
@@ -92,6 +92,7 @@ struct b3d_ctx {
     // ICP
     b3d::DevBuf grid_slots, grid_cursor, grid_pts, grid_nrm, pt_slot, pt_rank, partials;
     b3d::DevBuf nn_idx, nn_d2;
+    b3d::DevBuf src_slots, src_sorted, src_slot, src_rank;   // source reordered by target cell (coherent warps)
 
     // device scalars + pinned host mirror
     b3d::DevBuf state;                       // b3d::DeviceState

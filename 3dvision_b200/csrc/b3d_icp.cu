@@ -62,8 +62,11 @@ __device__ __forceinline__ unsigned long long pack_cell(int cx, int cy, int cz) 
            (unsigned long long)(unsigned)(cz + kCoordBias);
 }
 __device__ __forceinline__ unsigned hash_cell(unsigned long long k) {
-    k ^= k >> 33; k *= 0xff51afd7ed558ccdULL; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL; k ^= k >> 33;
-    return (unsigned)k;
+    // three 32-bit multiplies by large odd constants + a final fold; the full 64-bit key is what gets
+    // compared in the table, so hash quality only affects probe lengths, never results
+    const unsigned x = (unsigned)(k >> 42), y = (unsigned)(k >> 21) & 0x1FFFFFu, z = (unsigned)k & 0x1FFFFFu;
+    unsigned h = x * 73856093u ^ y * 19349669u ^ z * 83492791u;
+    return h ^ (h >> 15);
 }
 
 __global__ void grid_bounds_kernel(const float4* __restrict__ pts, unsigned n, GridParams* gp) {
@@ -75,6 +78,12 @@ __global__ void grid_bounds_kernel(const float4* __restrict__ pts, unsigned n, G
 #pragma unroll
     for (int s = 16; s >= 1; s >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));
     if ((threadIdx.x & 31) == 0 && isfinite(m)) atomicMax(&gp->max_abs_bits, __float_as_uint(m));
+}
+
+__global__ void slots_clear_kernel(CellSlot* slots, unsigned capacity) {
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < capacity; i += gridDim.x * blockDim.x) {
+        slots[i].key = kEmptyKey; slots[i].start = 0u; slots[i].count = 0u;
+    }
 }
 
 __global__ void grid_init_kernel(CellSlot* slots, unsigned capacity, GridParams* gp, float thr, unsigned n_points) {
@@ -96,8 +105,16 @@ __global__ void grid_init_kernel(CellSlot* slots, unsigned capacity, GridParams*
 
 // claim a slot + a rank inside the cell; one atomicAdd per distinct cell per warp
 __global__ void grid_insert_kernel(const float4* __restrict__ pts, unsigned n, CellSlot* slots, const GridParams* __restrict__ gp,
+                                   unsigned mask, const float* __restrict__ T_or_null,
                                    unsigned* __restrict__ pt_slot, unsigned* __restrict__ pt_rank) {
-    const float inv = gp->inv_cell; const unsigned mask = gp->mask;
+    const float inv = gp->inv_cell;
+    float Tm[12];
+    if (T_or_null) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) Tm[r * 4 + cc] = T_or_null[cc * 4 + r];
+    }
     const unsigned lane = threadIdx.x & 31;
     const unsigned total = (n + 31u) & ~31u;
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -105,6 +122,12 @@ __global__ void grid_insert_kernel(const float4* __restrict__ pts, unsigned n, C
         unsigned slot = 0xFFFFFFFFu;
         if (live) {
             float4 p = pts[i];
+            if (T_or_null) {
+                float x = Tm[0] * p.x + Tm[1] * p.y + Tm[2] * p.z + Tm[3];
+                float y = Tm[4] * p.x + Tm[5] * p.y + Tm[6] * p.z + Tm[7];
+                float z = Tm[8] * p.x + Tm[9] * p.y + Tm[10] * p.z + Tm[11];
+                p.x = x; p.y = y; p.z = z;
+            }
             unsigned long long key = pack_cell(cell_coord(p.x, inv), cell_coord(p.y, inv), cell_coord(p.z, inv));
             slot = hash_cell(key) & mask;
             while (true) {
@@ -175,28 +198,41 @@ __device__ __forceinline__ void visit_cell(const GridView& g, int cx, int cy, in
 // Nearest target of p within the 27-cell neighbourhood: lexicographic (d2, index) minimum.
 // The query's own cell is searched first; a neighbour cell is skipped when even its nearest face
 // (shrunk by `slack` to cover rounding in the cell assignment) is farther than the best match so
-// far, which cannot change the minimum or its tie-break.
+// far, which cannot change the minimum or its tie-break.  The face tests are evaluated branch-free
+// into a 27-bit mask and the surviving neighbours are then visited in compacted order, so the
+// lanes of a warp stay converged for max(popcount) rounds instead of the union of their subsets.
 __device__ __forceinline__ void grid_nearest(float px, float py, float pz, const GridView& g,
                                              float& best_d2, unsigned& best_idx, unsigned& best_pos) {
     best_d2 = FLT_MAX; best_idx = B3D_NO_MATCH; best_pos = 0u;
     const int cx = cell_coord(px, g.inv), cy = cell_coord(py, g.inv), cz = cell_coord(pz, g.inv);
     visit_cell(g, cx, cy, cz, px, py, pz, best_d2, best_idx, best_pos);
-    // distance from p to the low / high faces of its cell along each axis, made conservative
-    const float lox = fmaxf(px - (float)cx * g.cell - g.slack, 0.0f), hix = fmaxf((float)(cx + 1) * g.cell - px - g.slack, 0.0f);
-    const float loy = fmaxf(py - (float)cy * g.cell - g.slack, 0.0f), hiy = fmaxf((float)(cy + 1) * g.cell - py - g.slack, 0.0f);
-    const float loz = fmaxf(pz - (float)cz * g.cell - g.slack, 0.0f), hiz = fmaxf((float)(cz + 1) * g.cell - pz - g.slack, 0.0f);
-    for (int dz = -1; dz <= 1; ++dz) {
-        const float gz = dz < 0 ? loz : (dz > 0 ? hiz : 0.0f);
-        for (int dy = -1; dy <= 1; ++dy) {
-            const float gy = dy < 0 ? loy : (dy > 0 ? hiy : 0.0f);
-            for (int dx = -1; dx <= 1; ++dx) {
-                if ((dx | dy | dz) == 0) continue;
-                const float gx = dx < 0 ? lox : (dx > 0 ? hix : 0.0f);
-                const float gap2 = __fmul_rd(gx, gx) + (__fmul_rd(gy, gy) + __fmul_rd(gz, gz));
-                if (gap2 * 0.999f > best_d2) continue;
-                visit_cell(g, cx + dx, cy + dy, cz + dz, px, py, pz, best_d2, best_idx, best_pos);
-            }
-        }
+    // squared distance from p to the low / high faces of its cell along each axis, made conservative
+    float f2[3][3];                                                // [axis][0: low side, 1: same, 2: high side]
+    {
+        const float lo0 = fmaxf(px - (float)cx * g.cell - g.slack, 0.0f), hi0 = fmaxf((float)(cx + 1) * g.cell - px - g.slack, 0.0f);
+        const float lo1 = fmaxf(py - (float)cy * g.cell - g.slack, 0.0f), hi1 = fmaxf((float)(cy + 1) * g.cell - py - g.slack, 0.0f);
+        const float lo2 = fmaxf(pz - (float)cz * g.cell - g.slack, 0.0f), hi2 = fmaxf((float)(cz + 1) * g.cell - pz - g.slack, 0.0f);
+        f2[0][0] = __fmul_rd(lo0, lo0) * 0.999f; f2[0][1] = 0.0f; f2[0][2] = __fmul_rd(hi0, hi0) * 0.999f;
+        f2[1][0] = __fmul_rd(lo1, lo1) * 0.999f; f2[1][1] = 0.0f; f2[1][2] = __fmul_rd(hi1, hi1) * 0.999f;
+        f2[2][0] = __fmul_rd(lo2, lo2) * 0.999f; f2[2][1] = 0.0f; f2[2][2] = __fmul_rd(hi2, hi2) * 0.999f;
+    }
+    unsigned todo = 0u;
+#pragma unroll
+    for (int k = 0; k < 27; ++k) {
+        if (k == 13) continue;
+        const float gap2 = f2[0][k % 3] + (f2[1][(k / 3) % 3] + f2[2][k / 9]);      // indices fold at compile time
+        todo |= (gap2 > best_d2 ? 0u : 1u) << k;
+    }
+    while (todo) {
+        const int k = __ffs(todo) - 1;
+        todo &= todo - 1u;
+        const int dx = k % 3 - 1, dy = (k / 3) % 3 - 1, dz = k / 9 - 1;
+        // the best may have improved since the mask was built: re-test before paying for the probe
+        const float gx = dx < 0 ? f2[0][0] : (dx > 0 ? f2[0][2] : 0.0f);
+        const float gy = dy < 0 ? f2[1][0] : (dy > 0 ? f2[1][2] : 0.0f);
+        const float gz = dz < 0 ? f2[2][0] : (dz > 0 ? f2[2][2] : 0.0f);
+        if (gx + (gy + gz) > best_d2) continue;
+        visit_cell(g, cx + dx, cy + dy, cz + dz, px, py, pz, best_d2, best_idx, best_pos);
     }
 }
 
@@ -361,7 +397,7 @@ icp_accumulate_kernel(const float4* __restrict__ src, unsigned n_src, const Devi
 }
 
 // one block: fixed-order sum of the block partials, solve, update T / result / flags
-constexpr int kUpdateThreads = 256;
+constexpr int kUpdateThreads = 1024;
 template <bool PLANE>
 __global__ void __launch_bounds__(kUpdateThreads)
 icp_update_kernel(const double* __restrict__ partials, int n_blocks, int iter, float n_src_f, int stop_on_convergence,
@@ -373,6 +409,7 @@ icp_update_kernel(const double* __restrict__ partials, int n_blocks, int iter, f
     {
         const int v = threadIdx.x % kPartialStride, gidx = threadIdx.x / kPartialStride;
         double s = 0.0;
+#pragma unroll 8
         for (int b = gidx; b < n_blocks; b += kUpdateThreads / kPartialStride) s += partials[(size_t)b * kPartialStride + v];
         grp[gidx][v] = s;
     }
@@ -455,7 +492,8 @@ static int build_grid(b3d_ctx* c, float thr, GridParams** gp_out, unsigned* capa
     grid_init_kernel<<<grid_for(capacity, 256, 4), 256, 0, c->stream>>>(slots, capacity, gp, thr, n);
     B3D_LAUNCHED(c);
     if (n) {
-        grid_insert_kernel<<<grid_for(n, 256, 8), 256, 0, c->stream>>>(c->tgt4.as<float4>(), n, slots, gp, c->pt_slot.as<unsigned>(), c->pt_rank.as<unsigned>());
+        grid_insert_kernel<<<grid_for(n, 256, 8), 256, 0, c->stream>>>(c->tgt4.as<float4>(), n, slots, gp, capacity - 1u, nullptr,
+                                                                       c->pt_slot.as<unsigned>(), c->pt_rank.as<unsigned>());
         B3D_LAUNCHED(c);
         const unsigned tiles = (unsigned)div_up(capacity, kScanTile);
         B3D_CUDA(c, c->scan_tmp.ensure(sizeof(unsigned) * (tiles + 1)));
@@ -472,6 +510,39 @@ static int build_grid(b3d_ctx* c, float thr, GridParams** gp_out, unsigned* capa
         B3D_LAUNCHED(c);
     }
     *gp_out = gp; *capacity_out = capacity;
+    return B3D_OK;
+}
+
+// Reorder the source so that queries falling into the same target cell (under the initial transform)
+// are adjacent: the lanes of a warp then probe the same hash slots and scan the same cell points
+// (L1 hits / broadcast instead of scattered L2 reads) and run similar trip counts.  Pure scheduling:
+// the sums are order-independent up to fp64 rounding and every per-point result is unchanged.
+static int bin_source_by_cell(b3d_ctx* c, const GridParams* gp, const float* T_dev, const float4** src_out) {
+    const unsigned n = (unsigned)c->n_src;
+    const unsigned capacity = pow2_at_least(2 * (size_t)n);
+    B3D_CUDA(c, c->src_slots.ensure(sizeof(CellSlot) * capacity));
+    B3D_CUDA(c, c->src_sorted.ensure(sizeof(float4) * n));
+    B3D_CUDA(c, c->src_slot.ensure(sizeof(unsigned) * n));
+    B3D_CUDA(c, c->src_rank.ensure(sizeof(unsigned) * n));
+    CellSlot* slots = c->src_slots.as<CellSlot>();
+    slots_clear_kernel<<<grid_for(capacity, 256, 4), 256, 0, c->stream>>>(slots, capacity);
+    B3D_LAUNCHED(c);
+    grid_insert_kernel<<<grid_for(n, 256, 8), 256, 0, c->stream>>>(c->src4.as<float4>(), n, slots, gp, capacity - 1u, T_dev,
+                                                                   c->src_slot.as<unsigned>(), c->src_rank.as<unsigned>());
+    B3D_LAUNCHED(c);
+    const unsigned tiles = (unsigned)div_up(capacity, kScanTile);
+    B3D_CUDA(c, c->scan_tmp.ensure(sizeof(unsigned) * (tiles + 1)));
+    SlotCount cnt{slots}; SlotStart st{slots};
+    scan_tile_sums_kernel<<<tiles, kScanThreads, 0, c->stream>>>(cnt, capacity, c->scan_tmp.as<unsigned>());
+    B3D_LAUNCHED(c);
+    scan_tile_offsets_kernel<<<1, kScanThreads, 0, c->stream>>>(c->scan_tmp.as<unsigned>(), tiles, (unsigned*)nullptr);
+    B3D_LAUNCHED(c);
+    scan_emit_kernel<<<tiles, kScanThreads, 0, c->stream>>>(cnt, st, capacity, c->scan_tmp.as<unsigned>());
+    B3D_LAUNCHED(c);
+    grid_scatter_kernel<<<grid_for(n, 256, 8), 256, 0, c->stream>>>(c->src4.as<float4>(), nullptr, n, slots, c->src_slot.as<unsigned>(),
+                                                                    c->src_rank.as<unsigned>(), c->src_sorted.as<float4>(), nullptr);
+    B3D_LAUNCHED(c);
+    *src_out = c->src_sorted.as<float4>();
     return B3D_OK;
 }
 
@@ -494,6 +565,12 @@ int icp_run_impl(b3d_ctx* c, const float* T0, float thr, int max_iter, int p2pla
     B3D_LAUNCHED(c);
 
     const unsigned n_src = (unsigned)c->n_src;
+    const float4* src = c->src4.as<float4>();
+    if (n_src >= 16384) {                                    // below that the reorder costs more than it saves
+        StageTimer timer(c, 6);
+        rc = bin_source_by_cell(c, gp, st->out18, &src);
+        if (rc != B3D_OK) return rc;
+    }
     const int blocks = div_up(n_src, kIcpThreads);           // one query per thread
     B3D_CUDA(c, c->partials.ensure(sizeof(double) * kPartialStride * (size_t)blocks));
     {
@@ -501,13 +578,13 @@ int icp_run_impl(b3d_ctx* c, const float* T0, float thr, int max_iter, int p2pla
         const CellSlot* slots = c->grid_slots.as<CellSlot>();
         for (int iter = 0; iter < max_iter; ++iter) {
             if (plane) {
-                icp_accumulate_kernel<true><<<blocks, kIcpThreads, 0, c->stream>>>(c->src4.as<float4>(), n_src, st, thr, slots, c->grid_pts.as<float4>(),
+                icp_accumulate_kernel<true><<<blocks, kIcpThreads, 0, c->stream>>>(src, n_src, st, thr, slots, c->grid_pts.as<float4>(),
                                                                                    c->grid_nrm.as<float4>(), gp, c->partials.as<double>());
                 B3D_LAUNCHED(c);
                 icp_update_kernel<true><<<1, kUpdateThreads, 0, c->stream>>>(c->partials.as<double>(), blocks, iter, (float)c->n_src, stop_on_conv, st);
                 B3D_LAUNCHED(c);
             } else {
-                icp_accumulate_kernel<false><<<blocks, kIcpThreads, 0, c->stream>>>(c->src4.as<float4>(), n_src, st, thr, slots, c->grid_pts.as<float4>(),
+                icp_accumulate_kernel<false><<<blocks, kIcpThreads, 0, c->stream>>>(src, n_src, st, thr, slots, c->grid_pts.as<float4>(),
                                                                                     c->grid_nrm.as<float4>(), gp, c->partials.as<double>());
                 B3D_LAUNCHED(c);
                 icp_update_kernel<false><<<1, kUpdateThreads, 0, c->stream>>>(c->partials.as<double>(), blocks, iter, (float)c->n_src, stop_on_conv, st);

@@ -13,5 +13,5 @@ for name, kw, thr_scale in [("C2 300k x 100k thr 5mm", {}, 1.0), ("C2 thr 1mm", 
         t0 = time.perf_counter()
         T, fit, rmse, it = ctx.icp_run(ic.T_init, thr, 50, plane, False)
         wall = time.perf_counter() - t0
-        print(f"{name:26s} plane={plane} iters={it} build={ctx.stage_ms(4)*1e3:7.1f} us  loop={ctx.stage_ms(5):8.3f} ms  per-iter={ctx.stage_ms(5)/50*1e3:7.1f} us "
+        print(f"{name:26s} plane={plane} iters={it} build={ctx.stage_ms(4)*1e3:6.1f}+{max(ctx.stage_ms(6),0)*1e3:5.1f} us  loop={ctx.stage_ms(5):8.3f} ms  per-iter={ctx.stage_ms(5)/50*1e3:7.1f} us "
               f"wall={wall*1e3:7.2f} ms fit={fit:.4f} rot_err={syn.rotation_error(T, ic.T_true):.2e}")
