@@ -1,0 +1,160 @@
+"""BASELINE.json's full-size configurations on the GPU.  The CPU oracle cannot run these sizes in a unit
+test, so parity is checked (a) bit-exactly on bounded slices the oracle can afford (rows, hypothesis-id
+ranges, source-point prefixes — every figure is independent per row / hypothesis / point), (b) between
+independent GPU kernels that share no screening arithmetic, and (c) through size-independent properties
+(determinism, permutation invariance, known ground truth)."""
+import importlib
+import threading
+
+import numpy as np
+import pytest
+
+syn = importlib.import_module("3dvision_b200.synthetic")
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def c3():
+    return syn.ransac_case()          # configs[2]: 100k x 100k descriptors, H = 1M
+
+
+def test_c3_matching_full_size(ctx, oracle, c3):
+    ctx.set_clouds(c3.source, c3.target); ctx.set_features(c3.source_desc, c3.target_desc)
+    ctx.set_match_mode(2); ctx.match_features()
+    corr = ctx.get_correspondences().copy()
+    ctx.match_features()
+    assert np.array_equal(corr, ctx.get_correspondences())                 # deterministic / idempotent
+    rows = np.random.default_rng(0).choice(c3.source.shape[0], 160, replace=False)
+    for r in rows:                                                          # oracle on a bounded slice of rows
+        assert corr[r] == oracle.match_features(c3.source_desc, c3.target_desc, int(r), int(r) + 1)[0]
+    ctx.set_match_mode(1)
+    ctx.set_correspondences(np.zeros(c3.source.shape[0], np.uint32))
+    ctx.match_features(70_000, 73_000)                                      # exact CUDA-core kernel on a row range
+    assert np.array_equal(ctx.get_correspondences()[70_000:73_000], corr[70_000:73_000])
+    ctx.set_match_mode(0)
+    inl = c3.true_match >= 0
+    assert (corr[inl] == c3.true_match[inl]).mean() > 0.995
+
+
+def test_c3_scoring_full_size(ctx, oracle, c3):
+    """1M hypotheses: RNG stream / Lemire compaction / Kabsch / counts checked against the oracle on id ranges at the
+    start, middle and very end of the stream; packed-FFMA2 screen vs un-fused kernel on 60k hypotheses."""
+    corr = np.where(c3.true_match >= 0, c3.true_match, 0).astype(np.uint32)
+    H = c3.max_iterations
+    ctx.set_clouds(c3.source, c3.target); ctx.set_correspondences(corr)
+    ctx.ransac_prepare(c3.voxel_size, H, 2.0)
+    for lo in (0, 500_000, H - 48):
+        hi = lo + 48
+        ctx.set_score_mode(0); ctx.ransac_score(lo, hi)
+        got = ctx.ransac_counts(lo, hi)
+        ref = oracle.ransac(c3.source, c3.target, corr, c3.voxel_size, H, 2.0, iter_lo=lo, iter_hi=hi, want_counts=True)
+        assert np.array_equal(got, ref.extra["counts"][lo:hi]), f"counts differ in [{lo},{hi})"
+    ctx.set_score_mode(0); ctx.ransac_score(200_000, 260_000); a = ctx.ransac_counts(200_000, 260_000)
+    assert ctx.score_recounts() > 0                                          # the band path was exercised
+    ctx.set_score_mode(2); ctx.ransac_score(200_000, 260_000); b = ctx.ransac_counts(200_000, 260_000)
+    ctx.set_score_mode(1); ctx.ransac_score(200_000, 260_000); c = ctx.ransac_counts(200_000, 260_000)
+    ctx.set_score_mode(0)
+    assert np.array_equal(a, c) and np.array_equal(b, c)
+    assert c.max() > 0.5 * c3.source.shape[0]                                # good hypotheses exist in that range
+
+
+def test_c3_near_threshold_pairs_stress_the_band(ctx, oracle):
+    """Noise comparable to the inlier threshold puts many pairs inside the screening band; counts must stay exact."""
+    c = syn.ransac_case(n_src=20_000, n_tgt=15_000, seed=55, noise=0.0009, max_iterations=3000)
+    corr = np.where(c.true_match >= 0, c.true_match, 0).astype(np.uint32)
+    ctx.set_clouds(c.source, c.target); ctx.set_correspondences(corr)
+    ctx.ransac_prepare(c.voxel_size, 3000, 2.0); ctx.ransac_score()
+    ref = oracle.ransac(c.source, c.target, corr, c.voxel_size, 3000, 2.0, want_counts=True)
+    assert np.array_equal(ctx.ransac_counts(), ref.extra["counts"])
+    assert ctx.score_recounts() > 1000
+
+
+@pytest.fixture(scope="module")
+def c2():
+    return syn.icp_case()             # configs[1]: 300k scene vs 100k model
+
+
+def test_c2_icp_full_size(ctx, oracle, c2):
+    ctx.set_clouds(c2.source, c2.target, c2.target_normals)
+    idx, d2 = ctx.icp_nearest(c2.T_init, c2.threshold)
+    n = 2500                                                                # oracle brute force on a prefix of the source
+    ref = oracle.icp(c2.source[:n], c2.target, c2.target_normals, c2.T_init, c2.threshold, 1, True, want_nn0=True)
+    kept = np.sqrt(ref.extra["nn_d2_0"]) <= np.float32(c2.threshold)
+    assert kept.sum() > 2000
+    assert np.array_equal(idx[:n][kept], ref.extra["nn_idx0"][kept]) and np.array_equal(d2[:n][kept], ref.extra["nn_d2_0"][kept])
+    assert (idx[:n][~kept] == 0xFFFFFFFF).all()
+    T, fit, rmse, it = ctx.icp_run(c2.T_init, c2.threshold, c2.iterations, True, False)
+    T2, fit2, rmse2, _ = ctx.icp_run(c2.T_init, c2.threshold, c2.iterations, True, False)
+    assert np.array_equal(T, T2) and fit == fit2 and rmse == rmse2          # run-to-run deterministic (fixed-order sums)
+    assert it == c2.iterations and fit > 0.99
+    assert syn.rotation_error(T, c2.T_true) < 3e-4 and syn.translation_error(T, c2.T_true) < 5e-5
+    perm = np.random.default_rng(1).permutation(c2.source.shape[0])         # source order must not matter
+    ctx.set_clouds(c2.source[perm], c2.target, c2.target_normals)
+    T3, fit3, _, _ = ctx.icp_run(c2.T_init, c2.threshold, c2.iterations, True, False)
+    assert fit3 == fit and syn.rotation_error(T3, T) < 1e-6 and syn.translation_error(T3, T) < 1e-7
+    tperm = np.random.default_rng(2).permutation(c2.target.shape[0])        # target order only relabels indices
+    ctx.set_clouds(c2.source, c2.target[tperm], c2.target_normals[tperm])
+    idx_p, d2_p = ctx.icp_nearest(c2.T_init, c2.threshold)
+    assert np.array_equal(d2_p, d2)
+    m = idx != 0xFFFFFFFF
+    assert np.array_equal(c2.target[tperm][idx_p[m]], c2.target[idx[m]])
+
+
+def test_c4_batched_instances_from_a_thread_pool(b3d, oracle):
+    """configs[3] in miniature: independent instances registered concurrently from pool threads, each thread with its
+    own context (the orchestrator's contract, pipeline.cpp:321-327). Every instance must equal the oracle."""
+    n_inst, results, errors = 16, {}, []
+
+    def work(i):
+        try:
+            c = syn.ransac_case(n_src=1200 + 37 * i, n_tgt=900 + 11 * i, seed=1000 + i, max_iterations=1200)
+            src = b3d.PointCloud(points=c.source); tgt = b3d.PointCloud(points=c.target, normals=c.target_normals)
+            coarse = b3d.Registration.ransacRegistration(src, tgt, b3d.FPFHFeatures(c.source_desc), b3d.FPFHFeatures(c.target_desc),
+                                                         c.voxel_size, c.max_iterations)
+            fine = b3d.GPURegistration.icpRefine(src, tgt, coarse.transformation, 0.004, 10)
+            results[i] = (c, coarse, fine)
+        except Exception as e:            # noqa: BLE001
+            errors.append((i, repr(e)))
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(n_inst)]
+    for k in range(0, n_inst, 8):
+        for t in threads[k:k + 8]:
+            t.start()
+        for t in threads[k:k + 8]:
+            t.join()
+    assert not errors, errors
+    for i, (c, coarse, fine) in results.items():
+        ref = oracle.ransac_registration(c.source, c.target, c.source_desc, c.target_desc, c.voxel_size, c.max_iterations, 0.999)
+        assert np.array_equal(coarse.transformation, ref.transformation) and coarse.fitness == ref.fitness and coarse.rmse == ref.rmse, i
+        refi = oracle.icp(c.source, c.target, c.target_normals, ref.transformation, 0.004, 10, True)
+        assert fine.fitness == refi.fitness, i
+        assert syn.rotation_error(fine.transformation, refi.transformation) < 1e-5
+        assert syn.translation_error(fine.transformation, refi.transformation) < 1e-6
+
+
+def test_c5_large_source_cloud(ctx, oracle):
+    """configs[4] scale on the hot path: 2M-point source (30 % outliers) against a 200k-point model."""
+    rng = np.random.default_rng(77)
+    model, nrm = syn.torus(200_000, rng, R=0.3, r=0.1)
+    n = 2_000_000
+    pick = rng.integers(0, model.shape[0], n)
+    T_true = syn.rigid([0.5, 0.1, 0.8], 12.0, [0.02, 0.01, -0.03])
+    src = syn.apply(np.linalg.inv(T_true), model[pick] + rng.normal(0, 2e-4, (n, 3)).astype(np.float32))
+    out = rng.random(n) < 0.3
+    src[out] = rng.uniform(src.min(0), src.max(0), (int(out.sum()), 3)).astype(np.float32)
+    T0 = (syn.rigid([0.1, 0.9, 0.2], 0.3, [0.0008, -0.0005, 0.0006]) @ T_true).astype(np.float32)
+    ctx.set_clouds(src, model, nrm)
+    idx, d2 = ctx.icp_nearest(T0, 0.003)
+    T, fit, rmse, it = ctx.icp_run(T0, 0.003, 12, True, True)
+    assert 0.6 < fit < 0.8 and it >= 2
+    assert syn.rotation_error(T, T_true) < 5e-4 and syn.translation_error(T, T_true) < 1e-4
+    k = 1500                                                                 # oracle on a prefix: exact NN + exact inlier counts
+    ref = oracle.icp(src[:k], model, nrm, T0, 0.003, 1, True, want_nn0=True)
+    kept = np.sqrt(ref.extra["nn_d2_0"]) <= np.float32(0.003)
+    assert np.array_equal(idx[:k][kept], ref.extra["nn_idx0"][kept]) and (idx[:k][~kept] == 0xFFFFFFFF).all()
+    corr = np.where(out, 0, pick).astype(np.uint32)
+    ctx.set_correspondences(corr)
+    ctx.ransac_prepare(0.001, 600, 2.0); ctx.ransac_score()
+    got = ctx.ransac_counts()
+    refr = oracle.ransac(src, model, corr, 0.001, 600, 2.0, iter_lo=0, iter_hi=24, want_counts=True)
+    assert np.array_equal(got[:24], refr.extra["counts"][:24])
