@@ -478,17 +478,24 @@ __global__ void select_kernel(const int* __restrict__ counts, int h0, int h1, fl
 // a single thread adds them left to right.
 // ---------------------------------------------------------------------------------
 constexpr int kFinishThreads = 1024;
+constexpr int kFinishProducers = kFinishThreads - 32;      // warps 0..30 evaluate pairs, warp 31 lane 0 adds (highest-id warp
+                                                           // wins issue arbitration on its sub-partition)
+constexpr int kFinishPer = 4;                              // consecutive pairs per producer thread per tile
+constexpr int kFinishTile = kFinishProducers * kFinishPer; // 3968 pairs: amortises the per-tile latency
 
+// One block, software-pipelined: the 31 producer warps evaluate a tile of pairs with the reference
+// arithmetic and compact the inliers' err^2 IN ORDER into one of two shared buffers while a single
+// consumer thread adds the previous tile left to right — the reference's sequential fp32 sum
+// (registration.cpp:277) cannot be re-associated without changing its bits, so the dependent FADD
+// chain (one add per inlier) is the floor; everything else is hidden behind it.
 __global__ void __launch_bounds__(kFinishThreads)
 finish_kernel(const long long* __restrict__ key_ptr, const float* __restrict__ hyp, int H,
               const float4* __restrict__ pairs, unsigned n_pairs, unsigned pair_stride,
               float n_src_f, float thr, DeviceState* __restrict__ st) {
-    __shared__ float vals[kFinishThreads];
-    __shared__ unsigned warp_cnt[kFinishThreads / 32];
-    __shared__ unsigned tile_total;
-    __shared__ float running;
-    __shared__ int inlier_total;
-    const int tid = threadIdx.x;
+    __shared__ __align__(16) float vals[2][kFinishTile];
+    __shared__ unsigned tile_count[2];
+    __shared__ unsigned warp_cnt[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     unsigned long long key = (unsigned long long)(*key_ptr);
     float* out = st->out18;
     if (key == 0ull) {                                 // no hypothesis ever beat fitness 0
@@ -502,44 +509,67 @@ finish_kernel(const long long* __restrict__ key_ptr, const float* __restrict__ h
     for (int e = 0; e < 9; ++e) R[e] = hyp[(size_t)e * H + h];
 #pragma unroll
     for (int e = 0; e < 3; ++e) t[e] = hyp[(size_t)(9 + e) * H + h];
-    if (tid == 0) { running = 0.0f; inlier_total = 0; }
-    __syncthreads();
-    for (unsigned base = 0; base < n_pairs; base += kFinishThreads) {
-        unsigned i = base + tid;
-        float e2 = 0.0f; bool in = false;
-        if (i < n_pairs) {
-            float4 s = pairs[i], q = pairs[pair_stride + i];
-            float x = (R[0] * s.x + (R[1] * s.y + R[2] * s.z)) + t[0];
-            float y = (R[3] * s.x + (R[4] * s.y + R[5] * s.z)) + t[1];
-            float z = (R[6] * s.x + (R[7] * s.y + R[8] * s.z)) + t[2];
-            float dx = x - q.x, dy = y - q.y, dz = z - q.z;
-            float err = sqrtf(dx * dx + (dy * dy + dz * dz));
-            in = err < thr;
-            e2 = err * err;
-        }
-        unsigned ballot = __ballot_sync(0xffffffffu, in);
-        unsigned lane = tid & 31, warp = tid >> 5;
-        if (lane == 0) warp_cnt[warp] = __popc(ballot);
-        __syncthreads();
-        if (warp == 0) {
-            unsigned c = warp_cnt[lane];
-            unsigned inc = warp_inclusive_scan(c);
-            warp_cnt[lane] = inc - c;
-            if (lane == 31) tile_total = inc;
-        }
-        __syncthreads();
-        if (in) vals[warp_cnt[warp] + __popc(ballot & ((1u << lane) - 1u))] = e2;
-        __syncthreads();
-        if (tid == 0) {
-            float acc = running; unsigned m = tile_total;
-            for (unsigned k = 0; k < m; ++k) acc += vals[k];
+    const unsigned n_tiles = (n_pairs + kFinishTile - 1) / kFinishTile;
+    float running = 0.0f;
+    int inlier_total = 0;
+    for (unsigned tile = 0; tile <= n_tiles; ++tile) {
+        if (warp < 31 && tile < n_tiles) {
+            // ---- producers: tile `tile` -> buffer tile & 1 ----
+            const unsigned i0 = tile * kFinishTile + (unsigned)tid * kFinishPer;
+            float e2[kFinishPer]; bool in[kFinishPer]; unsigned mine = 0;
+#pragma unroll
+            for (int j = 0; j < kFinishPer; ++j) {
+                e2[j] = 0.0f; in[j] = false;
+                if (i0 + j < n_pairs) {
+                    float4 s = pairs[i0 + j], q = pairs[pair_stride + i0 + j];
+                    float x = (R[0] * s.x + (R[1] * s.y + R[2] * s.z)) + t[0];
+                    float y = (R[3] * s.x + (R[4] * s.y + R[5] * s.z)) + t[1];
+                    float z = (R[6] * s.x + (R[7] * s.y + R[8] * s.z)) + t[2];
+                    float dx = x - q.x, dy = y - q.y, dz = z - q.z;
+                    float err = sqrtf(dx * dx + (dy * dy + dz * dz));
+                    in[j] = err < thr;
+                    e2[j] = err * err;
+                    mine += in[j] ? 1u : 0u;
+                }
+            }
+            const unsigned inc_lane = warp_inclusive_scan(mine);           // ordered: thread order == pair order
+            if (lane == 31) warp_cnt[warp] = inc_lane;
+            asm volatile("bar.sync 1, %0;" ::"n"(kFinishProducers) : "memory");
+            if (warp == 0) {                           // exclusive scan of the 31 producer-warp counts
+                unsigned c = (lane < 31) ? warp_cnt[lane] : 0u;      // lane l holds warp l's count (warp 31 is the consumer)
+                unsigned inc = warp_inclusive_scan(c);
+                warp_cnt[lane] = inc - c;
+                if (lane == 31) tile_count[tile & 1] = inc;
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(kFinishProducers) : "memory");
+            unsigned at = warp_cnt[warp] + inc_lane - mine;
+#pragma unroll
+            for (int j = 0; j < kFinishPer; ++j) if (in[j]) vals[tile & 1][at++] = e2[j];
+        } else if (tid == kFinishProducers && tile > 0) {
+            // ---- consumer: adds tile - 1 left to right ----
+            const float* v = vals[(tile - 1) & 1];
+            const unsigned m = tile_count[(tile - 1) & 1];
+            float acc = running;
+            unsigned k = 0;
+            if (m >= 16) {                             // register ping-pong: the next 8 loads fly under the current 8 adds
+                float4 a0 = *reinterpret_cast<const float4*>(v), a1 = *reinterpret_cast<const float4*>(v + 4), b0, b1;
+                for (; k + 24 <= m; k += 16) {
+                    b0 = *reinterpret_cast<const float4*>(v + k + 8);  b1 = *reinterpret_cast<const float4*>(v + k + 12);
+                    acc += a0.x; acc += a0.y; acc += a0.z; acc += a0.w; acc += a1.x; acc += a1.y; acc += a1.z; acc += a1.w;
+                    a0 = *reinterpret_cast<const float4*>(v + k + 16); a1 = *reinterpret_cast<const float4*>(v + k + 20);
+                    acc += b0.x; acc += b0.y; acc += b0.z; acc += b0.w; acc += b1.x; acc += b1.y; acc += b1.z; acc += b1.w;
+                }
+                acc += a0.x; acc += a0.y; acc += a0.z; acc += a0.w; acc += a1.x; acc += a1.y; acc += a1.z; acc += a1.w;
+                k += 8;
+            }
+            for (; k < m; ++k) acc += v[k];
             running = acc;
             inlier_total += (int)m;
         }
-        __syncthreads();
+        __syncthreads();                               // tile produced / previous tile consumed
     }
-    if (tid == 0) {
-        int inliers = inlier_total;   // recounted here: the winner may have been scored on another rank
+    if (tid == kFinishProducers) {
+        int inliers = inlier_total;                    // recounted here: the winner may have been scored on another rank
         float fitness = (float)inliers / n_src_f;
         float rmse = inliers > 0 ? sqrtf(running / (float)inliers) : 999.0f;
         // Matrix4f column-major: T(r,c) at c*4 + r
