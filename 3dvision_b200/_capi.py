@@ -156,7 +156,13 @@ class Context:
 
     # ---- plumbing ----
     def set_stream(self, cuda_stream: int | None):
-        self._check(self._L.b3d_ctx_set_stream(self._h, _vp(cuda_stream) if cuda_stream else None))
+        """Run on an external cudaStream_t. ``0`` (torch's default stream handle) selects the legacy default
+        stream (cudaStreamLegacy == 0x1); ``None`` restores the context's own non-blocking stream."""
+        if cuda_stream is None:
+            arg = None
+        else:
+            arg = _vp(cuda_stream if cuda_stream != 0 else 1)
+        self._check(self._L.b3d_ctx_set_stream(self._h, arg))
 
     @property
     def kernel_launches(self) -> int:

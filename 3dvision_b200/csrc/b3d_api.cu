@@ -287,6 +287,7 @@ int b3d_ransac_counts(b3d_ctx* c, int h0, int h1, int32_t* out_host) {
     if (!c->prepared) return fail(c, B3D_ERR_STATE, "ransac_counts: not prepared");
     if (h0 < 0 || h1 > c->H || h0 > h1) return fail(c, B3D_ERR_INVALID, "ransac_counts: bad range");
     B3D_CUDA(c, cudaSetDevice(c->device));
+    { int rc = ransac_generate_impl(c, h0, h1); if (rc != B3D_OK) return rc; }   // degenerate-triple flags need the hypotheses
     if (h1 > h0 && c->n_src) B3D_CUDA(c, cudaMemcpyAsync(out_host, c->counts.as<int>() + h0, sizeof(int) * (size_t)(h1 - h0), cudaMemcpyDeviceToHost, c->stream));
     B3D_CUDA(c, cudaStreamSynchronize(c->stream));
     for (int h = h0; h < h1; ++h) {
@@ -303,6 +304,7 @@ int b3d_ransac_hypotheses(b3d_ctx* c, int h0, int h1, float* out_host) {
     if (h0 < 0 || h1 > c->H || h0 > h1) return fail(c, B3D_ERR_INVALID, "ransac_hypotheses: bad range");
     B3D_CUDA(c, cudaSetDevice(c->device));
     if (h1 == h0 || c->n_src == 0) return B3D_OK;
+    { int rc = ransac_generate_impl(c, h0, h1); if (rc != B3D_OK) return rc; }
     const size_t n = (size_t)(h1 - h0);
     float* tmp = nullptr;
     B3D_CUDA(c, cudaMallocHost(&tmp, sizeof(float) * 12 * n));

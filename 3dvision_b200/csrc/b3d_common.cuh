@@ -83,6 +83,7 @@ struct b3d_ctx {
     b3d::DevBuf pairs;                       // float4 [2][n_src]: (s_i, 0), (q_corr[i], 0)
     b3d::DevBuf seqsum;                      // float scratch for the exact sequential rmse sum
     int H = 0;
+    int hyp_lo = 0, hyp_hi = 0;              // id range whose (R,t) have been generated since the last prepare
     unsigned pair_stride = 0;                // pair array stride (n_src rounded up to the pair tile)
     int score_mode = 0;                      // 0 = FMA screen + exact band re-count, 1 = un-fused arithmetic everywhere
     float ransac_thr = 0.f, ransac_cut = 0.f, confidence = 0.f;
@@ -137,6 +138,7 @@ struct StageTimer {
 int match_features_impl(b3d_ctx* c, size_t row0, size_t row1);
 int match_features_tc_impl(b3d_ctx* c, size_t row0, size_t row1);
 int ransac_prepare_impl(b3d_ctx* c, float voxel, int max_iterations, float confidence);
+int ransac_generate_impl(b3d_ctx* c, int h0, int h1);
 int ransac_score_impl(b3d_ctx* c, int h0, int h1);
 int ransac_reduce_impl(b3d_ctx* c, int h0, int h1, const int64_t* limit_key_dev, int64_t* keys_dev);
 int ransac_finish_impl(b3d_ctx* c, const int64_t* keys_dev, float* T, float* fitness, float* rmse, int32_t* best);

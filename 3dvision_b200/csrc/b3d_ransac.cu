@@ -78,10 +78,10 @@ __global__ void gather_pairs_kernel(const float4* __restrict__ src4, const float
 // hypothesis generation: hyp is SoA float[12][H]
 // ---------------------------------------------------------------------------------
 __global__ void hypothesis_kernel(const uint32_t* __restrict__ draws, const DeviceState* __restrict__ st,
-                                  const float4* __restrict__ pairs, unsigned pair_stride, int H,
+                                  const float4* __restrict__ pairs, unsigned pair_stride, int H, int h_lo, int h_hi,
                                   float* __restrict__ hyp, int* __restrict__ counts) {
-    int h = blockIdx.x * blockDim.x + threadIdx.x;
-    if (h >= H) return;
+    int h = h_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= h_hi) return;
     if ((unsigned)(3 * h + 2) >= st->accepted_total) { counts[h] = -3; return; }   // raw window too small
     uint32_t i0 = draws[3 * h], i1 = draws[3 * h + 1], i2 = draws[3 * h + 2];
     if (i0 == i1 || i1 == i2 || i0 == i2) {                // registration.cpp:240 `continue`
@@ -489,7 +489,7 @@ constexpr int kFinishTile = kFinishProducers * kFinishPer; // 3968 pairs: amorti
 // (registration.cpp:277) cannot be re-associated without changing its bits, so the dependent FADD
 // chain (one add per inlier) is the floor; everything else is hidden behind it.
 __global__ void __launch_bounds__(kFinishThreads)
-finish_kernel(const long long* __restrict__ key_ptr, const float* __restrict__ hyp, int H,
+finish_kernel(const long long* __restrict__ key_ptr, const uint32_t* __restrict__ draws,
               const float4* __restrict__ pairs, unsigned n_pairs, unsigned pair_stride,
               float n_src_f, float thr, DeviceState* __restrict__ st) {
     __shared__ __align__(16) float vals[2][kFinishTile];
@@ -504,11 +504,28 @@ finish_kernel(const long long* __restrict__ key_ptr, const float* __restrict__ h
         return;
     }
     const int h = (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull));
+    // The winner may have been generated and scored on another rank: rebuild its (R,t) from the
+    // index triple with the same Kabsch code (bit-identical by construction).
+    __shared__ float Rt[12];
+    if (tid == 0) {
+        float s3[3][3], q3[3][3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const uint32_t id = draws[3 * h + k];
+            const float4 a = pairs[id], b = pairs[pair_stride + id];
+            s3[k][0] = a.x; s3[k][1] = a.y; s3[k][2] = a.z;
+            q3[k][0] = b.x; q3[k][1] = b.y; q3[k][2] = b.z;
+        }
+        Mat3 Rm; float tv[3];
+        kabsch_three_points(s3, q3, Rm, tv);
+        for (int r = 0; r < 3; ++r) { for (int cc = 0; cc < 3; ++cc) Rt[r * 3 + cc] = Rm(r, cc); Rt[9 + r] = tv[r]; }
+    }
+    __syncthreads();
     float R[9], t[3];
 #pragma unroll
-    for (int e = 0; e < 9; ++e) R[e] = hyp[(size_t)e * H + h];
+    for (int e = 0; e < 9; ++e) R[e] = Rt[e];
 #pragma unroll
-    for (int e = 0; e < 3; ++e) t[e] = hyp[(size_t)(9 + e) * H + h];
+    for (int e = 0; e < 3; ++e) t[e] = Rt[9 + e];
     const unsigned n_tiles = (n_pairs + kFinishTile - 1) / kFinishTile;
     float running = 0.0f;
     int inlier_total = 0;
@@ -658,9 +675,7 @@ int ransac_prepare_impl(b3d_ctx* c, float voxel, int max_iterations, float confi
                                                                                     c->pairs.as<float4>(), st);
             B3D_LAUNCHED(c);
         }
-        hypothesis_kernel<<<div_up(H, 128), 128, 0, c->stream>>>(c->draws.as<uint32_t>(), st, c->pairs.as<float4>(), pair_stride, H,
-                                                                   c->hyp.as<float>(), c->counts.as<int>());
-        B3D_LAUNCHED(c);
+        c->hyp_lo = c->hyp_hi = 0;          // hypotheses are generated lazily, per scored / inspected id range
         // The acceptance window is sized 8 sigma above the expectation; verify it on the host only
         // when rejections are frequent enough for that to matter (huge clouds).
         if (p_rej < 1e-3) break;
@@ -674,16 +689,41 @@ int ransac_prepare_impl(b3d_ctx* c, float voxel, int max_iterations, float confi
     return B3D_OK;
 }
 
+// 3-point Kabsch for ids [h0,h1) (registration.cpp:239-268).  Lazy so that a rank which scores only
+// its shard of the ids does not pay for everybody else's hypotheses.
+int ransac_generate_impl(b3d_ctx* c, int h0, int h1) {
+    if (h1 <= h0 || c->n_src == 0) return B3D_OK;
+    auto launch = [&](int a, int b) -> int {
+        if (b <= a) return B3D_OK;
+        hypothesis_kernel<<<div_up(b - a, 128), 128, 0, c->stream>>>(c->draws.as<uint32_t>(), c->state.as<DeviceState>(), c->pairs.as<float4>(),
+                                                                     c->pair_stride, c->H, a, b, c->hyp.as<float>(), c->counts.as<int>());
+        B3D_LAUNCHED(c);
+        return B3D_OK;
+    };
+    const bool have = c->hyp_hi > c->hyp_lo;
+    if (have && h0 <= c->hyp_hi && h1 >= c->hyp_lo) {          // overlaps / touches: generate only what is missing
+        int rc = launch(h0, min(h1, c->hyp_lo)); if (rc != B3D_OK) return rc;
+        rc = launch(max(h0, c->hyp_hi), h1); if (rc != B3D_OK) return rc;
+        c->hyp_lo = min(c->hyp_lo, h0); c->hyp_hi = max(c->hyp_hi, h1);
+    } else {                                                   // disjoint: track the new range (the old data stays valid but untracked)
+        int rc = launch(h0, h1); if (rc != B3D_OK) return rc;
+        c->hyp_lo = h0; c->hyp_hi = h1;
+    }
+    return B3D_OK;
+}
+
 int ransac_score_impl(b3d_ctx* c, int h0, int h1) {
     if (!c->prepared) return fail(c, B3D_ERR_STATE, "ransac_score: call ransac_prepare first");
     if (h0 < 0 || h1 > c->H || h0 > h1) return fail(c, B3D_ERR_INVALID, "ransac_score: bad hypothesis range");
     c->scored = true; c->scored_lo = h0; c->scored_hi = h1;
     if (h0 == h1 || c->n_src == 0) return B3D_OK;
     StageTimer timer(c, 2);
+    { int rc = ransac_generate_impl(c, h0, h1); if (rc != B3D_OK) return rc; }
     const unsigned n = (unsigned)c->n_src;
     const int nh = h1 - h0;
-    // KH = 2 hypotheses per thread when there are enough of them to fill the machine twice over
-    const int KH = (nh >= 2 * kNumSMs * kScoreThreads * 4) ? 2 : 1;
+    // two hypotheses per thread (one packed FFMA2 lane pair) unless there are hardly any; the pair-range
+    // split below supplies the parallelism when the id range is short (multi-GPU shards)
+    const int KH = (nh >= 2 * kScoreThreads) ? 2 : 1;
     const int bx = div_up(nh, kScoreThreads * KH);
     // Split the pair stream so that the grid is many waves deep: blocks are long-running and
     // compute-bound, so a shallow grid loses up to a full wave to the tail.
@@ -753,7 +793,7 @@ int ransac_finish_impl(b3d_ctx* c, const int64_t* keys_dev, float* T, float* fit
     }
     {
         StageTimer timer(c, 3);
-        finish_kernel<<<1, kFinishThreads, 0, c->stream>>>(reinterpret_cast<const long long*>(keys_dev), c->hyp.as<float>(), c->H,
+        finish_kernel<<<1, kFinishThreads, 0, c->stream>>>(reinterpret_cast<const long long*>(keys_dev), c->draws.as<uint32_t>(),
                                                            c->pairs.as<float4>(), (unsigned)c->n_src, c->pair_stride,
                                                            (float)c->n_src, c->ransac_thr, st);
         B3D_LAUNCHED(c);

@@ -57,7 +57,8 @@ int  b3d_ctx_create(int device, b3d_ctx** out);
 void b3d_ctx_destroy(b3d_ctx* ctx);
 
 /* Run all work of this context on an externally owned cudaStream_t (e.g. the
- * current torch stream) instead of the context's own stream. NULL restores it. */
+ * current torch stream) instead of the context's own stream. NULL restores the own
+ * stream; to select the legacy default stream pass cudaStreamLegacy ((void*)0x1). */
 int b3d_ctx_set_stream(b3d_ctx* ctx, void* cuda_stream);
 
 const char* b3d_strerror(int status);
