@@ -241,7 +241,7 @@ score_screen_kernel(const float* __restrict__ hyp, int H, int h0, int h1,
                              fmaxf(fabsf(R[k][3]) + fabsf(R[k][4]) + fabsf(R[k][5]), fabsf(R[k][6]) + fabsf(R[k][7]) + fabsf(R[k][8])));
         float A = rowsum * smax + fmaxf(fabsf(t[k][0]), fmaxf(fabsf(t[k][1]), fabsf(t[k][2]))) + qmax;
         float e = A * 7.152557373046875e-7f;                    // 12 * 2^-24 * A  (11 roundings per coordinate + margin)
-        float beta = 4.0f * (thr * 1.02f + e) * e + 2e-6f * cut;
+        float beta = 1.25f * (4.0f * (thr * 1.02f + e) * e + 2e-6f * cut);      // 25 % on top of the derived bound
         if (beta < 0.5f * cut) { lo[k] = cut - beta; hi[k] = cut + beta; }
         else { lo[k] = -INFINITY; hi[k] = INFINITY; }           // bound useless or NaN: every group is re-counted exactly
     }
@@ -318,7 +318,7 @@ __device__ __forceinline__ float screen_lo_hi(const float* R, const float* t, fl
     float rowsum = fmaxf(fabsf(R[0]) + fabsf(R[1]) + fabsf(R[2]), fmaxf(fabsf(R[3]) + fabsf(R[4]) + fabsf(R[5]), fabsf(R[6]) + fabsf(R[7]) + fabsf(R[8])));
     float A = rowsum * smax + fmaxf(fabsf(t[0]), fmaxf(fabsf(t[1]), fabsf(t[2]))) + qmax;
     float e = A * 7.152557373046875e-7f;                        // 12 * 2^-24 * A
-    float beta = 4.0f * (thr * 1.02f + e) * e + 2e-6f * cut;
+    float beta = 1.25f * (4.0f * (thr * 1.02f + e) * e + 2e-6f * cut);      // 25 % on top of the derived bound
     if (beta < 0.5f * cut) { lo = cut - beta; hi = cut + beta; } else { lo = -INFINITY; hi = INFINITY; }
     return beta;
 }
