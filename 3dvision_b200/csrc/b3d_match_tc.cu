@@ -19,8 +19,8 @@
 //              cp.async.bulk (TMA bulk copy, mbarrier complete_tx) and needs no tensor map
 //   pipeline : warp 0 = bulk-copy producer (3-stage B ring + A tile), warp 1 = single-thread
 //              tcgen05.mma issuer (M128 x N256 x K16, 7 k-steps, fp32 accumulators in TMEM,
-//              double-buffered: 2 x 256 columns), warps 2..9 = epilogue (tcgen05.ld 32x32b.x32,
-//              one TMEM lane = one source row per thread, 32-wide max-reduce + one compare)
+//              double-buffered: 2 x 256 columns), warps 2..17 = epilogue (two tcgen05.ld 32x32b.x32 in
+//              flight, one TMEM lane = one source row per thread, 3-input max tree + one compare)
 //   schedule : persistent, one CTA per SM, contiguous slice of the (row block, column tile) space
 //   error    : band_i = 2^-13 (|a_i| + max_j |b_j|)^2 covers the dropped a_lo.b_lo / residual
 //              terms (<= 3*2^-18 |a||b|), fp32 accumulation inside the tensor core over 112
@@ -38,7 +38,8 @@ constexpr int kTcN = 256;                  // target rows per tile (UMMA N)
 constexpr int kTcK = 112;                  // packed K' (7 x UMMA_K 16)
 constexpr int kTcChunks = kTcK / 8;        // 16-byte K chunks per row
 constexpr int kTcStages = 3;
-constexpr int kTcThreads = 320;            // producer + mma + 8 epilogue warps
+constexpr int kTcEpiWarps = 16;            // 4 TMEM lane quarters x 4 column parts of 64
+constexpr int kTcThreads = 64 + 32 * kTcEpiWarps;   // producer + mma + epilogue warps
 constexpr uint32_t kATileBytes = kTcM * kTcK * 2;     // 28 672
 constexpr uint32_t kBTileBytes = kTcN * kTcK * 2;     // 57 344
 constexpr uint32_t kTcSmemBytes = kATileBytes + kTcStages * kBTileBytes + 256 + 1024;
@@ -164,6 +165,17 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uin
                  "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                  ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+__device__ __forceinline__ void tc_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
     uint32_t r[32];
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -206,7 +218,7 @@ match_tc_kernel(const __nv_bfloat16* __restrict__ a_tiles, const __nv_bfloat16* 
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kTcStages; ++s) { mbar_init(BAR(s), 1); mbar_init(BAR(3 + s), 1); }
         mbar_init(BAR(6), 1); mbar_init(BAR(7), 1);
-        mbar_init(BAR(8), 8); mbar_init(BAR(9), 8);
+        mbar_init(BAR(8), kTcEpiWarps); mbar_init(BAR(9), kTcEpiWarps);
         mbar_init(BAR(10), 1); mbar_init(BAR(11), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -270,68 +282,80 @@ match_tc_kernel(const __nv_bfloat16* __restrict__ a_tiles, const __nv_bfloat16* 
             }
         }
     } else {
-        // ===== epilogue: thread = one source row (TMEM lane), 128 of the tile's 256 columns =====
+        // ===== epilogue: thread = one source row (TMEM lane), 64 of the tile's 256 columns =====
+        // The epilogue has to read every fp32 accumulator once: 128 KB of TMEM per tile at ~64 B/clk/SM is
+        // ~2000 cycles against 896 cycles of MMA, so this kernel is TMEM-read bound (measured: sharing each
+        // B tile across 4 row blocks to cut L2 traffic 4x did not help).
         const int ew = warp - 2;
         const int quarter = warp & 3;                      // TMEM lanes a warp may touch: 32 * (warpid % 4)
-        const int half = ew >> 2;
+        const int part = ew >> 2;                          // which 64-column slice
         const unsigned bad = aux->bad;
         const float bmax = __uint_as_float(aux->max_bnorm_bits);
         uint32_t acc = 0, acc_phase = 0;
-        unsigned cur_rb = 0xFFFFFFFFu;
-        unsigned i = 0; bool row_live = false; float na = 0.0f, band = 0.0f;
+        unsigned cur_rb = 0xFFFFFFFFu, since_refresh = 0;
+        unsigned i = 0; bool row_live = false; float na = 0.0f, band = 0.0f, best_d = FLT_MAX, u = INFINITY;
+        auto threshold = [&]() {
+            float t = bad ? -INFINITY : 0.5f * ((na - best_d) - band) - 1e-30f;
+            return (t == t) ? t : -INFINITY;               // NaN norm => re-score everything
+        };
+        auto rescore = [&](unsigned mask, unsigned colbase) {
+            while (mask) {
+                const int k = __ffs(mask) - 1;
+                mask &= mask - 1u;
+                const unsigned j = colbase + k;
+                if (j < n_tgt) {
+                    const float d = exact_dist(sdesc + (size_t)i * kDescDim, tdesc + (size_t)j * kDescDim);
+                    const unsigned long long key = pack_key(d, j);
+                    const unsigned long long old = atomicMin(&best[i], key);
+                    const float nd = __uint_as_float((unsigned)((old < key ? old : key) >> 32));
+                    if (nd < best_d) { best_d = nd; u = threshold(); }
+                }
+            }
+        };
         for (unsigned t = t_begin; t < t_end; ++t) {
             const unsigned rb = t / n_nt, nt = t - rb * n_nt;
             if (rb != cur_rb) {
-                cur_rb = rb;
+                cur_rb = rb; since_refresh = 1000;
                 i = (rb_first + rb) * kTcM + quarter * 32 + lane;
                 row_live = (i >= row0 && i < row1);
+                na = 0.0f; band = 0.0f;
                 if (row_live) {
                     na = a_norm2[i];
                     float s = sqrtf(na) * 1.0000002f + bmax;
                     band = kBandKappa * s * s;
                 }
             }
-            float best_d = 0.0f, u = INFINITY;
-            if (row_live) {
-                best_d = __uint_as_float((unsigned)(*(volatile unsigned long long*)&best[i] >> 32));
-                u = bad ? -INFINITY : 0.5f * ((na - best_d) - band) - 1e-30f;
-                if (!(u == u)) u = -INFINITY;              // NaN norm => re-score everything
+            if (++since_refresh >= 4) {                    // other warps tighten the row's best too; a stale value is only looser
+                since_refresh = 0;
+                best_d = row_live ? __uint_as_float((unsigned)(*(volatile unsigned long long*)&best[i] >> 32)) : 0.0f;
+                u = row_live ? threshold() : INFINITY;
             }
             mbar_wait(BAR(6 + acc), acc_phase);
             tc_fence_after();
-            const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * (uint32_t)kTcN + half * 128;
-            const unsigned col0 = nt * kTcN + half * 128;
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                float v[32];
-                __syncwarp();
-                tc_ld32(taddr0 + c * 32, v);
-                float m = v[0];
+            const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * (uint32_t)kTcN + part * 64;
+            const unsigned col0 = nt * kTcN + part * 64;
+            uint32_t r0[32], r1[32];
+            __syncwarp();
+            tc_ld32_issue(taddr0, r0);                     // both 32-column chunks in flight, one wait
+            tc_ld32_issue(taddr0 + 32, r1);
+            tc_ld_wait();
+            float m0 = __uint_as_float(r0[0]), m1 = __uint_as_float(r1[0]);
 #pragma unroll
-                for (int k = 1; k < 32; ++k) m = fmaxf(m, v[k]);
-                if (row_live && (bad || m >= u)) {                                 // rare: exact re-score
-                    unsigned mask = 0u;
+            for (int k = 1; k + 1 < 32; k += 2) {
+                m0 = fmaxf(m0, fmaxf(__uint_as_float(r0[k]), __uint_as_float(r0[k + 1])));
+                m1 = fmaxf(m1, fmaxf(__uint_as_float(r1[k]), __uint_as_float(r1[k + 1])));
+            }
+            m0 = fmaxf(m0, __uint_as_float(r0[31])); m1 = fmaxf(m1, __uint_as_float(r1[31]));
+            if (row_live && (bad || fmaxf(m0, m1) >= u)) {                         // rare: exact re-score
+                unsigned mask0 = 0u, mask1 = 0u;
 #pragma unroll
-                    for (int k = 0; k < 32; ++k) mask |= (v[k] >= u ? 1u : 0u) << k;
-                    if (bad) mask = 0xFFFFFFFFu;
-                    while (mask) {
-                        const int k = __ffs(mask) - 1;
-                        mask &= mask - 1u;
-                        {
-                            const unsigned j = col0 + c * 32 + k;
-                            if (j < n_tgt) {
-                                const float d = exact_dist(sdesc + (size_t)i * kDescDim, tdesc + (size_t)j * kDescDim);
-                                const unsigned long long key = pack_key(d, j);
-                                const unsigned long long old = atomicMin(&best[i], key);
-                                const float nd = __uint_as_float((unsigned)((old < key ? old : key) >> 32));
-                                if (nd < best_d) {
-                                    best_d = nd;
-                                    if (!bad) { u = 0.5f * ((na - best_d) - band) - 1e-30f; if (!(u == u)) u = -INFINITY; }
-                                }
-                            }
-                        }
-                    }
+                for (int k = 0; k < 32; ++k) {
+                    mask0 |= (__uint_as_float(r0[k]) >= u ? 1u : 0u) << k;
+                    mask1 |= (__uint_as_float(r1[k]) >= u ? 1u : 0u) << k;
                 }
+                if (bad) { mask0 = 0xFFFFFFFFu; mask1 = 0xFFFFFFFFu; }
+                rescore(mask0, col0);
+                rescore(mask1, col0 + 32);
             }
             tc_fence_before();
             __syncwarp();
