@@ -262,7 +262,8 @@ class Context:
         return int(p.value)
 
     def set_score_mode(self, mode: int):
-        """0 FMA screen + exact band re-count (default), 1 un-fused arithmetic everywhere (identical counts)."""
+        """0 packed FMA screen + exact band re-count (default), 1 un-fused arithmetic everywhere, 2 scalar FMA screen
+        (identical counts in all three); 3 bail-out: identical winner/result, hopeless hypotheses dropped part-way."""
         self._check(self._L.b3d_set_score_mode(self._h, mode))
 
     def ransac_prepare(self, voxel_size, max_iterations, confidence):

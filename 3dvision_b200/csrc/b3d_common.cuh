@@ -81,11 +81,12 @@ struct b3d_ctx {
     b3d::DevBuf hyp;                         // float [12][H] (SoA): R row-major 9, t 3
     b3d::DevBuf counts;                      // int32 [H]
     b3d::DevBuf pairs;                       // float4 [2][n_src]: (s_i, 0), (q_corr[i], 0)
+    b3d::DevBuf bail_list_a, bail_list_b, bail_state;   // bail-out scoring: survivor id lists + device plan
     b3d::DevBuf seqsum;                      // float scratch for the exact sequential rmse sum
     int H = 0;
     int hyp_lo = 0, hyp_hi = 0;              // id range whose (R,t) have been generated since the last prepare
     unsigned pair_stride = 0;                // pair array stride (n_src rounded up to the pair tile)
-    int score_mode = 0;                      // 0 = FMA screen + exact band re-count, 1 = un-fused arithmetic everywhere
+    int score_mode = 0;                      // 0 packed FMA screen, 1 un-fused everywhere, 2 scalar FMA screen, 3 bail-out (exact argmax)
     float ransac_thr = 0.f, ransac_cut = 0.f, confidence = 0.f;
     bool prepared = false, scored = false;
     int scored_lo = 0, scored_hi = 0;

@@ -185,6 +185,15 @@ score_exact_kernel(const float* __restrict__ hyp, int H, int h0, int h1,
 // branch-free.
 constexpr int kGroup = 32;
 
+__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v) {
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+        unsigned long long o = __shfl_xor_sync(0xffffffffu, v, m);
+        v = o > v ? o : v;
+    }
+    return v;
+}
+
 // One compare + one predicated add each (the compiler otherwise emits add-then-conditional-move
 // pairs; ALU-pipe instructions cost two issue cycles on this part, so they are worth trimming).
 __device__ __forceinline__ void count_below(int& cnt, float v, float bound) {       // cnt += (v < bound)
@@ -323,12 +332,29 @@ __device__ __forceinline__ float screen_lo_hi(const float* R, const float* t, fl
     return beta;
 }
 
+// Optional restriction of a scoring launch, decided ON THE DEVICE (bail-out phases): an id list instead
+// of the contiguous range, and a pair sub-range.  Null members mean "everything".
+struct ScoreSubset {
+    const int* list;            // hypothesis ids, or null for h0 + index
+    const int* n_list;          // number of ids in `list` (device scalar), or null for h1 - h0
+    const unsigned* prange;     // [lo, hi) pair range (multiples of the pair tile), or null for all pairs
+    int always_atomic;          // counts accumulate across launches
+};
+
 template <int KP>      // packed hypothesis pairs per thread (KH = 2 * KP hypotheses)
 __global__ void __launch_bounds__(kScoreThreads)
 score_screen2_kernel(const float* __restrict__ hyp, int H, int h0, int h1,
                      const float4* __restrict__ pairs, unsigned pair_stride, unsigned pairs_per_y,
-                     float cut, float thr, const DeviceState* __restrict__ st, int* __restrict__ counts) {
+                     float cut, float thr, const DeviceState* __restrict__ st, int* __restrict__ counts, ScoreSubset sub) {
     constexpr int KH = 2 * KP;
+    const int n_items = sub.n_list ? *sub.n_list : (h1 - h0);
+    if ((int)(blockIdx.x * KH * kScoreThreads) >= n_items) return;
+    unsigned r_lo = 0u, r_hi = pair_stride;
+    if (sub.prange) { r_lo = sub.prange[0]; r_hi = min(sub.prange[1], pair_stride); }
+    {
+        const unsigned yb = blockIdx.y * pairs_per_y;
+        if (max(yb, r_lo) >= min(yb + pairs_per_y, r_hi)) return;
+    }
     __shared__ float4 sP0[kPairTile];      // (sx, sx, sy, sy)
     __shared__ float4 sP1[kPairTile];      // (sz, sz, -qx, -qx)
     __shared__ float4 sP2[kPairTile];      // (-qy, -qy, -qz, -qz)
@@ -340,9 +366,10 @@ score_screen2_kernel(const float* __restrict__ hyp, int H, int h0, int h1,
     const float smax = __uint_as_float(st->pair_smax_bits), qmax = __uint_as_float(st->pair_qmax_bits);
 #pragma unroll
     for (int k = 0; k < KH; ++k) {
-        int h = h0 + (blockIdx.x * KH + k) * kScoreThreads + tid;
-        hid[k] = h;
-        int hc = h < h1 ? h : h1 - 1;
+        const int idx = (blockIdx.x * KH + k) * kScoreThreads + tid;
+        const int ic = idx < n_items ? idx : n_items - 1;
+        const int hc = sub.list ? sub.list[ic] : h0 + ic;
+        hid[k] = idx < n_items ? hc : -1;
 #pragma unroll
         for (int e = 0; e < 9; ++e) R[k][e] = hyp[(size_t)e * H + hc];
 #pragma unroll
@@ -357,8 +384,8 @@ score_screen2_kernel(const float* __restrict__ hyp, int H, int h0, int h1,
 #pragma unroll
         for (int e = 0; e < 3; ++e) tp[p][e] = pk2(t[2 * p][e], t[2 * p + 1][e]);
     }
-    const unsigned p_begin = blockIdx.y * pairs_per_y;
-    const unsigned p_end = min(pair_stride, p_begin + pairs_per_y);
+    const unsigned p_begin = max(blockIdx.y * pairs_per_y, r_lo);
+    const unsigned p_end = min(blockIdx.y * pairs_per_y + pairs_per_y, r_hi);
     for (unsigned base = p_begin; base < p_end; base += kPairTile) {
         __syncthreads();
         for (unsigned e = tid; e < kPairTile; e += kScoreThreads) {
@@ -419,8 +446,8 @@ score_screen2_kernel(const float* __restrict__ hyp, int H, int h0, int h1,
 #pragma unroll
     for (int k = 0; k < KH; ++k) {
         int h = hid[k];
-        if (h < h1 && counts[h] >= 0) {
-            if (gridDim.y == 1) counts[h] = total[k];
+        if (h >= 0 && counts[h] >= 0) {
+            if (gridDim.y == 1 && !sub.always_atomic) counts[h] = total[k];
             else if (total[k]) atomicAdd(&counts[h], total[k]);
         }
     }
@@ -428,16 +455,105 @@ score_screen2_kernel(const float* __restrict__ hyp, int H, int h0, int h1,
 }
 
 // ---------------------------------------------------------------------------------
+// Bail-out scoring (b3d_set_score_mode(ctx, 3)): the exact argmax without scoring every pair.
+// A hypothesis whose count so far plus the pairs not yet visited cannot reach the best FULL count
+// already known can neither win nor tie, so it is dropped (the classic RANSAC bail-out test, in
+// its exact form).  Everything is decided on the device; the host only enqueues a fixed sequence.
+//   phase 0: all ids on the first ~6 % of the pairs -> the id with the most inliers so far is scored
+//            on all pairs -> B (a true lower bound on the maximum)
+//   phase 1: all ids up to pair P1 = (1 - B/Nc + 2 %) Nc, the point where an id with no inlier at all
+//            becomes hopeless -> prune
+//   phase 2/3: survivors only, pruned once more in between.
+// The bound is capped at the smallest count whose fitness exceeds `confidence`, so a pruned id can
+// never be the one that would have triggered the reference's early exit (registration.cpp:290).
+// Pruned ids end with count -4; survivors and the phase-0 candidate carry exact full counts.
+// ---------------------------------------------------------------------------------
+struct BailState {
+    int B;                      // best full / partial count known (lower bound of the maximum)
+    int bound;                  // min(B, first count whose fitness > confidence)
+    int cand, cand_count;
+    int n_list[2];
+    unsigned prange[2];
+    unsigned p1, p2;
+    unsigned long long cand_key;
+};
+
+__global__ void bail_pick_kernel(const int* __restrict__ counts, int h0, int h1, BailState* bs) {
+    unsigned long long best = 0ull;
+    for (int h = h0 + blockIdx.x * blockDim.x + threadIdx.x; h < h1; h += gridDim.x * blockDim.x) {
+        int c = counts[h];
+        if (c < 0) continue;
+        unsigned long long key = ((unsigned long long)(unsigned)c << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)h);
+        best = key > best ? key : best;
+    }
+    best = warp_max_u64(best);
+    if ((threadIdx.x & 31) == 0 && best) atomicMax(&bs->cand_key, best);
+}
+
+// step = 0: after phase 0 -> candidate list of one id, all remaining pairs
+// step = 1: after the candidate's full score -> B, bound, P1; hide the candidate from later phases
+// step = 2: after the first prune -> range [P1, P2)        step = 3: after the second prune -> [P2, end)
+// step = 4: restore the candidate's exact count
+__global__ void bail_plan_kernel(int step, BailState* bs, int* counts, int* list_a, unsigned p0, unsigned stride, unsigned n_pairs,
+                                 float n_src_f, float confidence) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (step == 0) {
+        bs->cand = bs->cand_key ? (int)(0xFFFFFFFFu - (unsigned)(bs->cand_key & 0xFFFFFFFFull)) : -1;
+        list_a[0] = bs->cand < 0 ? 0 : bs->cand;
+        bs->n_list[0] = bs->cand < 0 ? 0 : 1;
+        bs->prange[0] = p0; bs->prange[1] = stride;
+    } else if (step == 1) {
+        bs->cand_count = bs->cand < 0 ? 0 : counts[bs->cand];
+        bs->B = bs->cand_count;
+        if (bs->cand >= 0) counts[bs->cand] = -5;                         // scored in full already: skip it in the phases
+        // smallest count whose fitness exceeds the confidence (never pruned below it)
+        int lo = 0, hi = (int)n_pairs + 1;                                 // fitness(hi) need not exceed: hi acts as "none"
+        while (lo < hi) { int mid = lo + (hi - lo) / 2; if ((float)mid / n_src_f > confidence) hi = mid; else lo = mid + 1; }
+        bs->bound = min(bs->B, lo);
+        float f1 = 1.0f - (float)bs->bound / (float)n_pairs + 0.02f;
+        unsigned p1 = (unsigned)(fminf(fmaxf(f1, 0.0f), 1.0f) * (float)n_pairs);
+        p1 = ((p1 + kPairTile - 1) / kPairTile) * kPairTile;
+        p1 = min(max(p1, p0), stride);
+        bs->p1 = p1; bs->p2 = min(stride, ((p1 + (stride - p1) / 2 + kPairTile - 1) / kPairTile) * kPairTile);
+        bs->prange[0] = p0; bs->prange[1] = p1;
+    } else if (step == 2) {
+        bs->prange[0] = bs->p1; bs->prange[1] = bs->p2;
+    } else if (step == 3) {
+        bs->prange[0] = bs->p2; bs->prange[1] = stride;
+    } else if (step == 4) {
+        if (bs->cand >= 0) counts[bs->cand] = bs->cand_count;
+    }
+}
+
+// keep ids that can still reach the bound; src == null means the contiguous range [h0,h1)
+__global__ void bail_prune_kernel(const int* __restrict__ src, const int* __restrict__ n_src_list, int h0, int h1, int* __restrict__ counts,
+                                  BailState* bs, int which_done /* 1: pairs < p1 visited, 2: pairs < p2 visited */, unsigned n_pairs,
+                                  int* __restrict__ dst, int* __restrict__ n_dst) {
+    const int n_items = src ? *n_src_list : (h1 - h0);
+    const unsigned done = min(which_done == 1 ? bs->p1 : bs->p2, n_pairs);
+    const int remaining = (int)(n_pairs - done);
+    const int bound = bs->bound;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    bool keep = false; int h = -1;
+    if (idx < n_items) {
+        h = src ? src[idx] : h0 + idx;
+        const int c = counts[h];
+        if (c >= 0) {
+            keep = c + remaining >= bound;
+            if (!keep) counts[h] = -4;
+        }
+    }
+    const unsigned ballot = __ballot_sync(0xffffffffu, keep);
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == 0 && ballot) base = atomicAdd(n_dst, __popc(ballot));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (keep) dst[base + __popc(ballot & ((1u << lane) - 1u))] = h;
+}
+
+// ---------------------------------------------------------------------------------
 // selection
 // ---------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v) {
-#pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) {
-        unsigned long long o = __shfl_xor_sync(0xffffffffu, v, m);
-        v = o > v ? o : v;
-    }
-    return v;
-}
 
 // mode 0: exit key (first id with fitness > confidence).  mode 1: best key over ids <= limit.
 __global__ void select_kernel(const int* __restrict__ counts, int h0, int h1, float n_src_f, float confidence,
@@ -712,6 +828,69 @@ int ransac_generate_impl(b3d_ctx* c, int h0, int h1) {
     return B3D_OK;
 }
 
+static int ransac_score_bailout(b3d_ctx* c, int h0, int h1) {
+    const unsigned n = (unsigned)c->n_src, stride = c->pair_stride;
+    const int nh = h1 - h0;
+    B3D_CUDA(c, c->bail_list_a.ensure(sizeof(int) * (size_t)nh));
+    B3D_CUDA(c, c->bail_list_b.ensure(sizeof(int) * (size_t)nh));
+    B3D_CUDA(c, c->bail_state.ensure(sizeof(BailState)));
+    BailState* bs = c->bail_state.as<BailState>();
+    int* counts = c->counts.as<int>();
+    int* la = c->bail_list_a.as<int>(); int* lb = c->bail_list_b.as<int>();
+    const float4* pairs = c->pairs.as<float4>();
+    const DeviceState* st = c->state.as<DeviceState>();
+    B3D_CUDA(c, cudaMemsetAsync(bs, 0, sizeof(BailState), c->stream));
+    B3D_CUDA(c, cudaMemsetAsync(&c->state.as<DeviceState>()->score_recounts, 0, sizeof(unsigned long long), c->stream));
+    reset_counts_kernel<<<div_up(nh, 256), 256, 0, c->stream>>>(counts, h0, h1);
+    B3D_LAUNCHED(c);
+    // launch geometry: worst case (every id, every pair); blocks outside the device-side subset return at once
+    const int bx = div_up(nh, kScoreThreads * 2);
+    int by = 1;
+    const int want_blocks = kNumSMs * 64;
+    if (bx < want_blocks) by = min(div_up(want_blocks, bx), div_up((long long)n, kPairTile * 4));
+    if (by < 1) by = 1;
+    unsigned per_y = (unsigned)div_up((long long)n, by);
+    per_y = (unsigned)div_up(per_y, kPairTile) * kPairTile;
+    by = div_up((long long)n, per_y);
+    auto score = [&](int gx, const int* list, const int* n_list) -> int {
+        score_screen2_kernel<1><<<dim3(gx, by), kScoreThreads, 0, c->stream>>>(c->hyp.as<float>(), c->H, h0, h1, pairs, stride, per_y, c->ransac_cut,
+                                                                               c->ransac_thr, st, counts, ScoreSubset{list, n_list, bs->prange, 1});
+        B3D_LAUNCHED(c);
+        return B3D_OK;
+    };
+    auto plan = [&](int step, unsigned p0) -> int {
+        bail_plan_kernel<<<1, 32, 0, c->stream>>>(step, bs, counts, la, p0, stride, n, (float)c->n_src, c->confidence);
+        B3D_LAUNCHED(c);
+        return B3D_OK;
+    };
+    unsigned p0 = (unsigned)div_up((long long)(0.06 * n), kPairTile) * kPairTile;
+    if (p0 > stride) p0 = stride;
+    int rc;
+    // phase 0: everyone on [0, p0)
+    const unsigned pr0[2] = {0u, p0};
+    B3D_CUDA(c, cudaMemcpyAsync(bs->prange, pr0, sizeof(pr0), cudaMemcpyHostToDevice, c->stream));
+    if ((rc = score(bx, nullptr, nullptr))) return rc;
+    bail_pick_kernel<<<grid_for(nh, 256, 4), 256, 0, c->stream>>>(counts, h0, h1, bs);
+    B3D_LAUNCHED(c);
+    if ((rc = plan(0, p0))) return rc;
+    if ((rc = score(1, la, &bs->n_list[0]))) return rc;                   // the candidate on every remaining pair
+    if ((rc = plan(1, p0))) return rc;                                     // B, bound, P1, range [p0, P1)
+    // phase 1: everyone on [p0, P1), then prune
+    if ((rc = score(bx, nullptr, nullptr))) return rc;
+    B3D_CUDA(c, cudaMemsetAsync(&bs->n_list[0], 0, 2 * sizeof(int), c->stream));
+    bail_prune_kernel<<<div_up(nh, 256), 256, 0, c->stream>>>(nullptr, nullptr, h0, h1, counts, bs, 1, n, la, &bs->n_list[0]);
+    B3D_LAUNCHED(c);
+    if ((rc = plan(2, p0))) return rc;
+    // phase 2: survivors on [P1, P2), prune again
+    if ((rc = score(bx, la, &bs->n_list[0]))) return rc;
+    bail_prune_kernel<<<div_up(nh, 256), 256, 0, c->stream>>>(la, &bs->n_list[0], h0, h1, counts, bs, 2, n, lb, &bs->n_list[1]);
+    B3D_LAUNCHED(c);
+    if ((rc = plan(3, p0))) return rc;
+    // phase 3: survivors on [P2, end)
+    if ((rc = score(bx, lb, &bs->n_list[1]))) return rc;
+    return plan(4, p0);
+}
+
 int ransac_score_impl(b3d_ctx* c, int h0, int h1) {
     if (!c->prepared) return fail(c, B3D_ERR_STATE, "ransac_score: call ransac_prepare first");
     if (h0 < 0 || h1 > c->H || h0 > h1) return fail(c, B3D_ERR_INVALID, "ransac_score: bad hypothesis range");
@@ -724,6 +903,7 @@ int ransac_score_impl(b3d_ctx* c, int h0, int h1) {
     // two hypotheses per thread (one packed FFMA2 lane pair) unless there are hardly any; the pair-range
     // split below supplies the parallelism when the id range is short (multi-GPU shards)
     const int KH = (nh >= 2 * kScoreThreads) ? 2 : 1;
+    if (c->score_mode == 3 && nh >= 8192 && n >= 16 * kPairTile) return ransac_score_bailout(c, h0, h1);
     const int bx = div_up(nh, kScoreThreads * KH);
     // Split the pair stream so that the grid is many waves deep: blocks are long-running and
     // compute-bound, so a shallow grid loses up to a full wave to the tail.
@@ -745,8 +925,8 @@ int ransac_score_impl(b3d_ctx* c, int h0, int h1) {
     if (c->score_mode == 1) {               // reference arithmetic for every pair (verification / comparison)
         if (KH == 2) score_exact_kernel<2><<<grid, kScoreThreads, 0, c->stream>>>(c->hyp.as<float>(), c->H, h0, h1, pairs, n, c->pair_stride, per_y, c->ransac_cut, c->counts.as<int>());
         else         score_exact_kernel<1><<<grid, kScoreThreads, 0, c->stream>>>(c->hyp.as<float>(), c->H, h0, h1, pairs, n, c->pair_stride, per_y, c->ransac_cut, c->counts.as<int>());
-    } else if (c->score_mode == 0) {        // packed FFMA2 screen (two hypotheses per instruction)
-        if (KH == 2) score_screen2_kernel<1><<<grid, kScoreThreads, 0, c->stream>>>(c->hyp.as<float>(), c->H, h0, h1, pairs, c->pair_stride, per_y, c->ransac_cut, c->ransac_thr, st, c->counts.as<int>());
+    } else if (c->score_mode == 0 || c->score_mode == 3) {   // packed FFMA2 screen (two hypotheses per instruction)
+        if (KH == 2) score_screen2_kernel<1><<<grid, kScoreThreads, 0, c->stream>>>(c->hyp.as<float>(), c->H, h0, h1, pairs, c->pair_stride, per_y, c->ransac_cut, c->ransac_thr, st, c->counts.as<int>(), ScoreSubset{nullptr, nullptr, nullptr, 0});
         else         score_screen_kernel<1><<<grid, kScoreThreads, 0, c->stream>>>(c->hyp.as<float>(), c->H, h0, h1, pairs, c->pair_stride, per_y, c->ransac_cut, c->ransac_thr, st, c->counts.as<int>());
     } else {                                // scalar FMA screen
         if (KH == 2) score_screen_kernel<2><<<grid, kScoreThreads, 0, c->stream>>>(c->hyp.as<float>(), c->H, h0, h1, pairs, c->pair_stride, per_y, c->ransac_cut, c->ransac_thr, st, c->counts.as<int>());

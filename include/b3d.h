@@ -122,8 +122,12 @@ int b3d_correspondences_devptr(b3d_ctx* ctx, void** out_devptr);
 /* src/registration.cpp:213, 235-268: threshold, RNG stream -> index triples,
  * 3-point Kabsch (R,t) for hypotheses [0,max_iterations). */
 int b3d_ransac_prepare(b3d_ctx* ctx, float voxel_size, int max_iterations, float confidence);
-/* Inlier-scoring kernel: 0 = FMA screen with exact re-count of pairs inside the error band
- * (default), 1 = the reference's un-fused arithmetic for every pair. Identical counts. */
+/* Inlier-scoring kernel: 0 = packed FMA screen with exact re-count of pairs inside the error band
+ * (default), 1 = the reference's un-fused arithmetic for every pair, 2 = scalar FMA screen; all
+ * three give identical counts for every hypothesis.  3 = bail-out: hypotheses that provably cannot
+ * reach the best full count found so far are dropped part-way (their count reads -4); the winner,
+ * its transform, fitness and rmse are identical to modes 0-2, per-hypothesis counts are not all
+ * available.  Not used by default. */
 int b3d_set_score_mode(b3d_ctx* ctx, int mode);
 /* src/registration.cpp:270-279 for hypothesis ids [h0,h1) (this rank's shard). */
 int b3d_ransac_score(b3d_ctx* ctx, int h0, int h1);

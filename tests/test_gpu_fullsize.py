@@ -158,3 +158,36 @@ def test_c5_large_source_cloud(ctx, oracle):
     got = ctx.ransac_counts()
     refr = oracle.ransac(src, model, corr, 0.001, 600, 2.0, iter_lo=0, iter_hi=24, want_counts=True)
     assert np.array_equal(got[:24], refr.extra["counts"][:24])
+
+
+def _staged_result(ctx, mode, voxel, H, confidence):
+    import torch
+    ctx.set_score_mode(mode)
+    try:
+        ctx.ransac_prepare(voxel, H, confidence)
+        ctx.ransac_score()
+        keys = torch.zeros(2, dtype=torch.int64, device="cuda")
+        torch.cuda.synchronize()
+        ctx.ransac_reduce(0, H, keys.data_ptr())
+        return ctx.ransac_finish(keys.data_ptr()), ctx.ransac_counts()
+    finally:
+        ctx.set_score_mode(0)
+
+
+@pytest.mark.parametrize("inlier_frac,confidence,H", [(0.7, 0.999, 20_000), (0.7, 0.30, 20_000), (0.15, 0.999, 12_000), (0.02, 0.999, 9_000)])
+def test_bailout_scoring_keeps_the_exact_winner(ctx, oracle, inlier_frac, confidence, H):
+    """score mode 3 drops hypotheses that provably cannot reach the best full count; the winner, its transform,
+    fitness, rmse and the early-exit behaviour must be identical to full scoring (and so to the oracle)."""
+    c = syn.ransac_case(n_src=30_000, n_tgt=20_000, seed=91, inlier_frac=inlier_frac, max_iterations=H)
+    corr = np.where(c.true_match >= 0, c.true_match, 0).astype(np.uint32)
+    ctx.set_clouds(c.source, c.target); ctx.set_correspondences(corr)
+    (T0, f0, r0, b0), counts_full = _staged_result(ctx, 0, c.voxel_size, H, confidence)
+    (T3, f3, r3, b3), counts_bail = _staged_result(ctx, 3, c.voxel_size, H, confidence)
+    assert b3 == b0 and np.array_equal(T3, T0) and f3 == f0 and r3 == r0
+    kept = counts_bail != -4
+    assert np.array_equal(counts_bail[kept], counts_full[kept])             # survivors carry exact full counts
+    assert counts_full[~kept].max(initial=-1) < counts_full.max()            # nothing that could win or tie was dropped
+    ref = oracle.ransac(c.source, c.target, corr, c.voxel_size, H, confidence)
+    assert b3 == ref.extra["best_iter"] and np.array_equal(T3, ref.transformation) and f3 == ref.fitness and r3 == ref.rmse
+    if inlier_frac >= 0.5:
+        assert (~kept).mean() > 0.3                                          # and it actually pruned
