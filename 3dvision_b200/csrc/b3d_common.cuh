@@ -94,6 +94,7 @@ struct b3d_ctx {
     // ICP
     b3d::DevBuf grid_slots, grid_cursor, grid_pts, grid_nrm, pt_slot, pt_rank, partials;
     b3d::DevBuf nn_idx, nn_d2;
+    b3d::DevBuf fine_slots, fine_pts;                        // second-level (finer) target grid
     b3d::DevBuf src_slots, src_sorted, src_slot, src_rank;   // source reordered by target cell (coherent warps)
 
     // device scalars + pinned host mirror
