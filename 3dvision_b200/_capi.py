@@ -29,7 +29,7 @@ SYMBOLS = [
     "b3d_ransac", "b3d_icp",
     "b3d_set_clouds", "b3d_set_features", "b3d_set_match_mode", "b3d_match_features", "b3d_get_correspondences", "b3d_get_correspondences_dev", "b3d_set_correspondences",
     "b3d_correspondences_devptr", "b3d_set_score_mode", "b3d_ransac_prepare", "b3d_ransac_score", "b3d_ransac_reduce", "b3d_ransac_finish",
-    "b3d_ransac_counts", "b3d_ransac_hypotheses", "b3d_icp_run", "b3d_icp_nearest",
+    "b3d_ransac_counts", "b3d_ransac_hypotheses", "b3d_set_icp_mode", "b3d_icp_run", "b3d_icp_nearest",
     "b3d_kernel_launches", "b3d_stage_ms", "b3d_measure_fp32_rate", "b3d_score_recounts",
 ]
 
@@ -80,6 +80,7 @@ def _declare(L):
     L.b3d_match_features.argtypes = [_vp, C.c_size_t, C.c_size_t]
     L.b3d_set_match_mode.argtypes = [_vp, C.c_int]
     L.b3d_set_score_mode.argtypes = [_vp, C.c_int]
+    L.b3d_set_icp_mode.argtypes = [_vp, C.c_int]
     L.b3d_get_correspondences.argtypes = [_vp, _vp]
     L.b3d_set_correspondences.argtypes = [_vp, _vp, C.c_int]
     L.b3d_get_correspondences_dev.argtypes = [_vp, _vp]
@@ -292,6 +293,10 @@ class Context:
         out = np.zeros((h1 - h0, 12), np.float32)
         self._check(self._L.b3d_ransac_hypotheses(self._h, h0, h1, _ptr(out)))
         return out
+
+    def set_icp_mode(self, mode: int):
+        """0 (default): point-to-point sums in the reference's order (fp32, sequential); 1: fp64 tree sums."""
+        self._check(self._L.b3d_set_icp_mode(self._h, mode))
 
     def icp_run(self, T0, distance_threshold, max_iterations=200, point_to_plane=True, stop_on_convergence=True):
         T0c = _T_colmajor(T0)

@@ -518,6 +518,168 @@ icp_update_kernel(const double* __restrict__ partials, int n_blocks, int iter, f
     if (stop_on_convergence && iter > 0 && fabsf(prev_rmse - rmse) < 1e-6f) st->done = 1;    // registration.cpp:406
 }
 
+// ---------------------------------------------------------------------------------
+// Reference-order point-to-point iteration (default for point-to-point).
+// The reference forms the centroids, the cross-covariance and total_error by adding one point at a
+// time in source order, in fp32 (registration.cpp:341, 374-386).  Point-to-point ICP converges
+// slowly, so the ~1e-6 m rounding noise of those sums is amplified to ~1e-4 in the final pose; the
+// only way to land inside the reference's own noise is to add in the same order.  So: the search
+// kernel stores every query's result at its ORIGINAL index, a prefix sum compacts the matched
+// (p, q) records in source order, and one block replays the reference's loops — 31 producer warps
+// stage tiles of records in shared memory while the lanes of one consumer warp each own one
+// running sum and add left to right (the dependent FADD chain is the floor).  Same solve as the
+// fast path afterwards.  b3d_set_icp_mode(ctx, 1) selects the fp64 tree sums instead.
+// ---------------------------------------------------------------------------------
+template <bool BINNED>
+__global__ void __launch_bounds__(kIcpThreads, 4)
+icp_search_kernel(const float4* __restrict__ src, unsigned n_src, const DeviceState* __restrict__ st, float thr,
+                  const CellSlot* __restrict__ slots, const float4* __restrict__ gpts,
+                  const CellSlot* __restrict__ fslots, const float4* __restrict__ fpts,
+                  const GridParams* __restrict__ gp, float4* __restrict__ rec, uint32_t* __restrict__ match) {
+    if (st->done) return;
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_src) return;
+    float R[9], t[3];
+    load_Rt(st->T, R, t);
+    const GridView g = make_view(slots, gpts, gp);
+    const GridView gfine = make_view(fslots, fpts, gp + 1);
+    const float4 s = src[i];
+    const unsigned orig = BINNED ? __float_as_uint(s.w) : i;
+    float x, y, z, d2; unsigned idx;
+    transform_point(R, t, s, x, y, z);
+    grid_nearest2(x, y, z, g, gfine, gp[1].enabled != 0u, gp[1].accept2, d2, idx);
+    const bool keep = idx != B3D_NO_MATCH && !(sqrtf(d2) > thr);            // registration.cpp:337-338
+    rec[orig] = make_float4(x, y, z, d2);
+    match[orig] = keep ? idx : B3D_NO_MATCH;
+}
+
+struct MatchFlag { const uint32_t* m; __device__ unsigned operator()(unsigned i) const { return m[i] != B3D_NO_MATCH ? 1u : 0u; } };
+struct CompactPairs {
+    const float4* rec; const uint32_t* m; const float4* tgt4; float4* outP; float4* outQ;
+    __device__ void operator()(unsigned i, unsigned prefix, unsigned flag) const {
+        if (flag) { outP[prefix] = rec[i]; outQ[prefix] = tgt4[m[i]]; }
+    }
+};
+
+constexpr int kSeqThreads = 1024;
+constexpr int kSeqTile = 512;
+constexpr int kSeqStride = kSeqTile + 1;      // +1: the 7 component arrays land in different banks
+
+__global__ void __launch_bounds__(kSeqThreads)
+icp_seq_p2p_kernel(const float4* __restrict__ P, const float4* __restrict__ Q, const unsigned* __restrict__ n_ptr,
+                   int iter, float n_src_f, int stop_on_convergence, DeviceState* __restrict__ st) {
+    if (st->done) return;
+    __shared__ float tile[2][7][kSeqStride];           // px py pz qx qy qz d2
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned n = *n_ptr;
+    if (n < 3u) { if (tid == 0) { st->n_corr_last = (int)n; st->done = 1; } return; }      // registration.cpp:361
+    const unsigned n_tiles = (n + kSeqTile - 1) / kSeqTile;
+    const bool consumer = warp == 31;                  // highest warp id wins issue arbitration on its sub-partition
+    float sums[2] = {0.0f, 0.0f};                      // lane's running sum in pass 0 / pass 1
+    float pm[3] = {0, 0, 0}, qm[3] = {0, 0, 0};
+    for (int pass = 0; pass < 2; ++pass) {
+        float acc = 0.0f;
+        const int r = lane / 3, cc = lane % 3;         // pass 1: lane < 9 owns H(r, cc)
+        for (unsigned t = 0; t <= n_tiles; ++t) {
+            if (!consumer && tid < kSeqTile && t < n_tiles) {
+                const unsigned k = t * kSeqTile + tid;
+                float4 p = make_float4(0, 0, 0, 0), q = make_float4(0, 0, 0, 0);
+                if (k < n) { p = P[k]; q = Q[k]; }
+                float (*b)[kSeqStride] = tile[t & 1];
+                b[0][tid] = p.x; b[1][tid] = p.y; b[2][tid] = p.z; b[3][tid] = q.x; b[4][tid] = q.y; b[5][tid] = q.z; b[6][tid] = p.w;
+            } else if (consumer && t > 0) {
+                const float (*b)[kSeqStride] = tile[(t - 1) & 1];
+                const unsigned m = min((unsigned)kSeqTile, n - (t - 1) * kSeqTile);
+                // register ping-pong: the next 8 operands are loaded (and, in pass 1, centred and multiplied)
+                // under the current 8 dependent adds; only real records are ever added (no padding terms)
+                if (pass == 0) {
+                    if (lane < 7) {                    // src_mean (3), tgt_mean (3), total_error
+                        const float* v = b[lane];
+                        unsigned k = 0;
+                        if (m >= 16) {
+                            float a[8], c8[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) a[j] = v[j];
+                            for (; k + 24 <= m; k += 16) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) c8[j] = v[k + 8 + j];
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) acc += a[j];
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) a[j] = v[k + 16 + j];
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) acc += c8[j];
+                            }
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) acc += a[j];
+                            k += 8;
+                        }
+                        for (; k < m; ++k) acc += v[k];
+                    }
+                } else if (lane < 9) {                 // H(r,cc) += (p_r - pm_r) * (q_cc - qm_cc)
+                    const float* vp = b[r]; const float* vq = b[3 + cc];
+                    const float mp = pm[r], mq = qm[cc];
+                    unsigned k = 0;
+                    if (m >= 16) {
+                        float a[8], c8[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) a[j] = (vp[j] - mp) * (vq[j] - mq);
+                        for (; k + 24 <= m; k += 16) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) c8[j] = (vp[k + 8 + j] - mp) * (vq[k + 8 + j] - mq);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) acc += a[j];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) a[j] = (vp[k + 16 + j] - mp) * (vq[k + 16 + j] - mq);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) acc += c8[j];
+                        }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) acc += a[j];
+                        k += 8;
+                    }
+                    for (; k < m; ++k) { const float a1 = vp[k] - mp, b1 = vq[k] - mq; acc += a1 * b1; }
+                }
+            }
+            __syncthreads();
+        }
+        sums[pass] = acc;
+        if (pass == 0) {                               // means: sum / float(n), registration.cpp:380-381
+            const float nf = (float)n;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                pm[a] = __shfl_sync(0xffffffffu, acc, a) / nf;
+                qm[a] = __shfl_sync(0xffffffffu, acc, 3 + a) / nf;
+            }
+        }
+    }
+    if (!consumer) return;
+    Mat3 H;
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) H(a, b) = __shfl_sync(0xffffffffu, sums[1], a * 3 + b);
+    const float total_error = __shfl_sync(0xffffffffu, sums[0], 6);
+    if (lane != 0) return;
+    st->n_corr_last = (int)n;
+    Mat3 dR; rotation_from_cross_covariance(H, dR);      // registration.cpp:388-394
+    float delta[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) delta[i] = (i % 5 == 0) ? 1.0f : 0.0f;
+    float r0, r1, r2; mat3_vec(dR, pm[0], pm[1], pm[2], r0, r1, r2);
+    for (int rr = 0; rr < 3; ++rr) for (int c2 = 0; c2 < 3; ++c2) delta[c2 * 4 + rr] = dR(rr, c2);
+    delta[12] = qm[0] - r0; delta[13] = qm[1] - r1; delta[14] = qm[2] - r2;             // registration.cpp:396
+    float Tn[16];
+    mat4_mul(delta, st->T, Tn);
+    const float prev_rmse = st->res_rmse;
+    const float rmse = sqrtf(total_error / (float)(int)n);
+    for (int i = 0; i < 16; ++i) { st->T[i] = Tn[i]; st->res_T[i] = Tn[i]; }
+    st->res_rmse = rmse;
+    st->res_fitness = (float)(int)n / n_src_f;
+    st->iterations = iter + 1;
+    if (stop_on_convergence && iter > 0 && fabsf(prev_rmse - rmse) < 1e-6f) st->done = 1;
+}
+
 __global__ void icp_state_init_kernel(DeviceState* st, const float* __restrict__ T0) {
     int i = threadIdx.x;
     if (i < 16) { st->T[i] = T0[i]; st->res_T[i] = T0[i]; }
@@ -642,7 +804,14 @@ int icp_run_impl(b3d_ctx* c, const float* T0, float thr, int max_iter, int p2pla
 
     const unsigned n_src = (unsigned)c->n_src;
     const float4* src = c->src4.as<float4>();
-    if (n_src >= 16384) {                                    // below that the reorder costs more than it saves
+    const bool binned = n_src >= 16384;
+    const unsigned seq_tiles = (unsigned)div_up(n_src, kScanTile);
+    if (!plane && c->icp_mode != 1) {
+        B3D_CUDA(c, c->seq_rec.ensure(sizeof(float4) * n_src)); B3D_CUDA(c, c->seq_match.ensure(sizeof(uint32_t) * n_src));
+        B3D_CUDA(c, c->seq_P.ensure(sizeof(float4) * n_src));   B3D_CUDA(c, c->seq_Q.ensure(sizeof(float4) * n_src));
+        B3D_CUDA(c, c->scan_tmp.ensure(sizeof(unsigned) * (seq_tiles + 1)));
+    }
+    if (binned) {                                            // below that the reorder costs more than it saves
         StageTimer timer(c, 6);
         rc = bin_source_by_cell(c, gp, st->out18, &src);
         if (rc != B3D_OK) return rc;
@@ -659,6 +828,23 @@ int icp_run_impl(b3d_ctx* c, const float* T0, float thr, int max_iter, int p2pla
                                                                                    c->tgt4.as<float4>(), c->nrm4.as<float4>(), gp, c->partials.as<double>());
                 B3D_LAUNCHED(c);
                 icp_update_kernel<true><<<1, kUpdateThreads, 0, c->stream>>>(c->partials.as<double>(), blocks, iter, (float)c->n_src, stop_on_conv, st);
+                B3D_LAUNCHED(c);
+            } else if (c->icp_mode != 1) {
+                // reference-order sums: search -> ordered compaction -> sequential replay (see icp_seq_p2p_kernel)
+                if (binned) icp_search_kernel<true><<<blocks, kIcpThreads, 0, c->stream>>>(src, n_src, st, thr, slots, c->grid_pts.as<float4>(), c->fine_slots.as<CellSlot>(),
+                                                                                           c->fine_pts.as<float4>(), gp, c->seq_rec.as<float4>(), c->seq_match.as<uint32_t>());
+                else        icp_search_kernel<false><<<blocks, kIcpThreads, 0, c->stream>>>(src, n_src, st, thr, slots, c->grid_pts.as<float4>(), c->fine_slots.as<CellSlot>(),
+                                                                                            c->fine_pts.as<float4>(), gp, c->seq_rec.as<float4>(), c->seq_match.as<uint32_t>());
+                B3D_LAUNCHED(c);
+                MatchFlag flag{c->seq_match.as<uint32_t>()};
+                CompactPairs emit{c->seq_rec.as<float4>(), c->seq_match.as<uint32_t>(), c->tgt4.as<float4>(), c->seq_P.as<float4>(), c->seq_Q.as<float4>()};
+                scan_tile_sums_kernel<<<seq_tiles, kScanThreads, 0, c->stream>>>(flag, n_src, c->scan_tmp.as<unsigned>());
+                B3D_LAUNCHED(c);
+                scan_tile_offsets_kernel<<<1, kScanThreads, 0, c->stream>>>(c->scan_tmp.as<unsigned>(), seq_tiles, &st->seq_count);
+                B3D_LAUNCHED(c);
+                scan_emit_kernel<<<seq_tiles, kScanThreads, 0, c->stream>>>(flag, emit, n_src, c->scan_tmp.as<unsigned>());
+                B3D_LAUNCHED(c);
+                icp_seq_p2p_kernel<<<1, kSeqThreads, 0, c->stream>>>(c->seq_P.as<float4>(), c->seq_Q.as<float4>(), &st->seq_count, iter, (float)c->n_src, stop_on_conv, st);
                 B3D_LAUNCHED(c);
             } else {
                 icp_accumulate_kernel<false><<<blocks, kIcpThreads, 0, c->stream>>>(src, n_src, st, thr, slots, c->grid_pts.as<float4>(),

@@ -145,6 +145,12 @@ int b3d_ransac_finish(b3d_ctx* ctx, const int64_t* keys_dev,
 int b3d_ransac_counts(b3d_ctx* ctx, int h0, int h1, int32_t* out_host);
 int b3d_ransac_hypotheses(b3d_ctx* ctx, int h0, int h1, float* out_host /* 12 per hypothesis */);
 
+/* Point-to-point accumulation: 0 (default) = add the matched pairs in source order in fp32, exactly
+ * as src/registration.cpp:341, 374-386 does (bit-identical sums; one sequential dependency chain per
+ * sum, so large clouds cost ~5 cycles per matched point per pass); 1 = deterministic fp64 tree sums
+ * (fast; differs from the reference by the reference's own rounding noise, ~1e-4 in the final pose).
+ * Point-to-plane always uses the fp64 tree sums (it meets 1e-5 / 1e-6 m with them). */
+int b3d_set_icp_mode(b3d_ctx* ctx, int mode);
 /* ICP on resident clouds. stop_on_convergence = 0 disables the |d rmse| < 1e-6 break
  * (src/registration.cpp:406) for fixed-iteration throughput runs. */
 int b3d_icp_run(b3d_ctx* ctx, const float T0_colmajor[16], float distance_threshold,

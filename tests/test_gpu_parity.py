@@ -16,12 +16,11 @@ pytestmark = pytest.mark.gpu
 
 ROT_TOL = 1e-5      # Frobenius norm of the rotation-block difference
 TRANS_TOL = 1e-6    # metres
-# Point-to-point mode only.  The reference accumulates the centroids and the cross-covariance
-# sequentially in fp32 (registration.cpp:374-386); over a few thousand points that sum carries
-# ~1e-6 m of rounding noise per iteration *in the reference itself*, and point-to-point ICP
-# converges slowly along the surface, so the noise is amplified to ~1e-4 by the time the
-# |d rmse| < 1e-6 stop fires.  The CUDA path accumulates in fp64 (deterministic, closer to the
-# exact sums), so it cannot land inside the reference's own noise; DESIGN.md "ICP parity".
+# Point-to-point with the fp64 tree sums (b3d_set_icp_mode 1) only.  The reference accumulates the centroids and
+# the cross-covariance sequentially in fp32 (registration.cpp:374-386); over a few thousand points that sum carries
+# ~1e-6 m of rounding noise per iteration *in the reference itself*, and point-to-point ICP converges slowly along
+# the surface, so the noise is amplified to ~1e-4 by the time the |d rmse| < 1e-6 stop fires.  The DEFAULT
+# point-to-point path replays the reference's summation order and is bit-identical to the oracle (tested below).
 P2P_ROT_TOL = 5e-4
 P2P_TRANS_TOL = 2e-4
 
@@ -200,29 +199,55 @@ def test_icp_nearest_ties_resolve_to_lowest_index(ctx, oracle):
     assert np.array_equal(d2, ref.extra["nn_d2_0"])
 
 
-@pytest.mark.parametrize("plane", [True, False])
-def test_icp_transform_within_tolerance(ctx, oracle, plane):
+def test_icp_point_to_plane_within_tolerance(ctx, oracle):
     case = icp_small()
-    ref = oracle.icp(case.source, case.target, case.target_normals, case.T_init, case.threshold, 30, plane)
-    T, fit, rmse, iters = ctx.icp(case.source, case.target, case.target_normals, case.T_init, case.threshold, 30, plane)
+    ref = oracle.icp(case.source, case.target, case.target_normals, case.T_init, case.threshold, 30, True)
+    T, fit, rmse, iters = ctx.icp(case.source, case.target, case.target_normals, case.T_init, case.threshold, 30, True)
     assert iters == ref.extra["iters_run"]
-    if plane:
-        assert fit == ref.fitness                           # same inlier set at the last iteration
-        assert abs(rmse - ref.rmse) < 1e-7
-    else:
-        assert abs(fit - ref.fitness) < 2e-3 and abs(rmse - ref.rmse) < 1e-6
-    assert syn.rotation_error(T, ref.transformation) < (ROT_TOL if plane else P2P_ROT_TOL)
-    assert syn.translation_error(T, ref.transformation) < (TRANS_TOL if plane else P2P_TRANS_TOL)
+    assert fit == ref.fitness                               # same inlier set at the last iteration
+    assert abs(rmse - ref.rmse) < 1e-7
+    assert syn.rotation_error(T, ref.transformation) < ROT_TOL
+    assert syn.translation_error(T, ref.transformation) < TRANS_TOL
     assert syn.rotation_error(T, case.T_true) < 1e-2        # and it converged to the real pose (sparse model)
+
+
+@pytest.mark.parametrize("iters", [1, 2, 5, 30])
+def test_icp_point_to_point_is_bit_identical(ctx, oracle, iters):
+    """Default point-to-point path adds in the reference's order: transform, fitness and rmse match the oracle bit for bit
+    at every iteration count (so the convergence break fires at the same iteration too)."""
+    case = icp_small()
+    ref = oracle.icp(case.source, case.target, case.target_normals, case.T_init, case.threshold, iters, False)
+    T, fit, rmse, it = ctx.icp(case.source, case.target, case.target_normals, case.T_init, case.threshold, iters, False)
+    assert it == ref.extra["iters_run"]
+    assert np.array_equal(T, ref.transformation) and fit == ref.fitness and rmse == ref.rmse
+
+
+def test_icp_point_to_point_large_binned_source_is_bit_identical(ctx, oracle):
+    """n_src >= 16384 takes the cell-binned query order; results are still written and summed in source order."""
+    case = syn.icp_case(n_model=3000, n_scene=20000, seed=61)
+    ref = oracle.icp(case.source, case.target, None, case.T_init, case.threshold, 6, False)
+    T, fit, rmse, it = ctx.icp(case.source, case.target, None, case.T_init, case.threshold, 6, False)
+    assert it == ref.extra["iters_run"] and np.array_equal(T, ref.transformation) and fit == ref.fitness and rmse == ref.rmse
+
+
+def test_icp_point_to_point_fast_mode_within_documented_tolerance(ctx, oracle):
+    case = icp_small()
+    ref = oracle.icp(case.source, case.target, case.target_normals, case.T_init, case.threshold, 30, False)
+    ctx.set_icp_mode(1)
+    try:
+        T, fit, rmse, iters = ctx.icp(case.source, case.target, case.target_normals, case.T_init, case.threshold, 30, False)
+    finally:
+        ctx.set_icp_mode(0)
+    assert iters == ref.extra["iters_run"] and abs(fit - ref.fitness) < 2e-3 and abs(rmse - ref.rmse) < 1e-6
+    assert syn.rotation_error(T, ref.transformation) < P2P_ROT_TOL and syn.translation_error(T, ref.transformation) < P2P_TRANS_TOL
 
 
 def test_icp_without_normals_falls_back_to_point_to_point(ctx, oracle):
     case = icp_small(seed=33, n_model=3000, n_scene=4000)
     ref = oracle.icp(case.source, case.target, None, case.T_init, case.threshold, 10, True)
     T, fit, rmse, iters = ctx.icp(case.source, case.target, None, case.T_init, case.threshold, 10, True)
-    assert iters == ref.extra["iters_run"] and abs(fit - ref.fitness) < 2e-3
-    assert syn.rotation_error(T, ref.transformation) < P2P_ROT_TOL
-    assert syn.translation_error(T, ref.transformation) < P2P_TRANS_TOL
+    assert iters == ref.extra["iters_run"] and fit == ref.fitness
+    assert np.array_equal(T, ref.transformation) and rmse == ref.rmse
 
 
 def test_icp_too_few_correspondences_keeps_initial(ctx, oracle):
