@@ -96,8 +96,8 @@ struct b3d_ctx {
     b3d::DevBuf grid_slots, grid_cursor, grid_pts, grid_nrm, pt_slot, pt_rank, partials;
     b3d::DevBuf nn_idx, nn_d2;
     b3d::DevBuf fine_slots, fine_pts;
-    b3d::DevBuf seq_rec, seq_match, seq_P, seq_Q;            // reference-order point-to-point: per-query records, compacted pairs
-    int icp_mode = 0;                                        // 0: point-to-point adds in the reference's order; 1: fp64 tree sums everywhere                        // second-level (finer) target grid
+    b3d::DevBuf seq_rec, seq_match, seq_P, seq_Q, seq_N;            // reference-order point-to-point: per-query records, compacted pairs
+    int icp_mode = 0;                                        // 0: point-to-point adds in the reference's order; 1: fp64 tree sums everywhere; 2: reference order for plane too                        // second-level (finer) target grid
     b3d::DevBuf src_slots, src_sorted, src_slot, src_rank;   // source reordered by target cell (coherent warps)
 
     // device scalars + pinned host mirror

@@ -556,8 +556,13 @@ icp_search_kernel(const float4* __restrict__ src, unsigned n_src, const DeviceSt
 struct MatchFlag { const uint32_t* m; __device__ unsigned operator()(unsigned i) const { return m[i] != B3D_NO_MATCH ? 1u : 0u; } };
 struct CompactPairs {
     const float4* rec; const uint32_t* m; const float4* tgt4; float4* outP; float4* outQ;
+    const float4* nrm4; float4* outN;              // point-to-plane replay only (else null)
     __device__ void operator()(unsigned i, unsigned prefix, unsigned flag) const {
-        if (flag) { outP[prefix] = rec[i]; outQ[prefix] = tgt4[m[i]]; }
+        if (flag) {
+            const uint32_t j = m[i];
+            outP[prefix] = rec[i]; outQ[prefix] = tgt4[j];
+            if (outN) outN[prefix] = nrm4[j];
+        }
     }
 };
 
@@ -669,6 +674,95 @@ icp_seq_p2p_kernel(const float4* __restrict__ P, const float4* __restrict__ Q, c
     float r0, r1, r2; mat3_vec(dR, pm[0], pm[1], pm[2], r0, r1, r2);
     for (int rr = 0; rr < 3; ++rr) for (int c2 = 0; c2 < 3; ++c2) delta[c2 * 4 + rr] = dR(rr, c2);
     delta[12] = qm[0] - r0; delta[13] = qm[1] - r1; delta[14] = qm[2] - r2;             // registration.cpp:396
+    float Tn[16];
+    mat4_mul(delta, st->T, Tn);
+    const float prev_rmse = st->res_rmse;
+    const float rmse = sqrtf(total_error / (float)(int)n);
+    for (int i = 0; i < 16; ++i) { st->T[i] = Tn[i]; st->res_T[i] = Tn[i]; }
+    st->res_rmse = rmse;
+    st->res_fitness = (float)(int)n / n_src_f;
+    st->iterations = iter + 1;
+    if (stop_on_convergence && iter > 0 && fabsf(prev_rmse - rmse) < 1e-6f) st->done = 1;
+}
+
+// Reference-order point-to-plane iteration (b3d_set_icp_mode(ctx, 2)): same pipeline as icp_seq_p2p_kernel for
+// registration.cpp:343-354.  Producers form J = [p x n | n] and r = (p - q).n per matched record with the
+// reference's un-fused arithmetic; lanes 0..20 of the consumer warp own the upper triangle of ATA (J_a*J_b is
+// commutative, so the lower triangle is bit-identical), lanes 21..26 own ATb, lane 27 owns total_error, and each adds
+// its products left to right in source order.  The 6x6 solve and the update are the fast path's.
+__global__ void __launch_bounds__(kSeqThreads)
+icp_seq_plane_kernel(const float4* __restrict__ P, const float4* __restrict__ Q, const float4* __restrict__ N,
+                     const unsigned* __restrict__ n_ptr, int iter, float n_src_f, int stop_on_convergence,
+                     DeviceState* __restrict__ st) {
+    if (st->done) return;
+    __shared__ float tile[2][8][kSeqStride];           // J0..J5, residual, d2
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned n = *n_ptr;
+    if (n < 3u) { if (tid == 0) { st->n_corr_last = (int)n; st->done = 1; } return; }      // registration.cpp:361
+    const unsigned n_tiles = (n + kSeqTile - 1) / kSeqTile;
+    const bool consumer = warp == 31;
+    int ra = 7, rb = 7; bool unit = true;              // lane 27 (and the idle lanes above it): d2 * 1
+    if (lane < 21) { int k = lane, a = 0; while (k >= 6 - a) { k -= 6 - a; ++a; } ra = a; rb = a + k; unit = false; }
+    else if (lane < 27) { ra = lane - 21; rb = 6; unit = false; }
+    float acc = 0.0f;
+    for (unsigned t = 0; t <= n_tiles; ++t) {
+        if (!consumer && tid < kSeqTile && t < n_tiles) {
+            const unsigned k = t * kSeqTile + tid;
+            float J0 = 0, J1 = 0, J2 = 0, J3 = 0, J4 = 0, J5 = 0, res = 0, d2 = 0;
+            if (k < n) {
+                const float4 p = P[k], q = Q[k], nn = N[k];
+                J0 = p.y * nn.z - p.z * nn.y; J1 = p.z * nn.x - p.x * nn.z; J2 = p.x * nn.y - p.y * nn.x;   // p.cross(n)
+                J3 = nn.x; J4 = nn.y; J5 = nn.z;
+                const float a0 = (p.x - q.x) * nn.x, a1 = (p.y - q.y) * nn.y, a2 = (p.z - q.z) * nn.z;
+                res = a0 + (a1 + a2);                                                                        // (p - q).dot(n)
+                d2 = p.w;
+            }
+            float (*b)[kSeqStride] = tile[t & 1];
+            b[0][tid] = J0; b[1][tid] = J1; b[2][tid] = J2; b[3][tid] = J3; b[4][tid] = J4; b[5][tid] = J5; b[6][tid] = res; b[7][tid] = d2;
+        } else if (consumer && t > 0 && lane < 28) {
+            const float (*b)[kSeqStride] = tile[(t - 1) & 1];
+            const unsigned m = min((unsigned)kSeqTile, n - (t - 1) * kSeqTile);
+            const float* va = b[ra]; const float* vb = b[rb];
+            unsigned k = 0;
+            if (m >= 16) {
+                float a[8], c8[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) a[j] = va[j] * (unit ? 1.0f : vb[j]);
+                for (; k + 24 <= m; k += 16) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) c8[j] = va[k + 8 + j] * (unit ? 1.0f : vb[k + 8 + j]);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc += a[j];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) a[j] = va[k + 16 + j] * (unit ? 1.0f : vb[k + 16 + j]);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc += c8[j];
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc += a[j];
+                k += 8;
+            }
+            for (; k < m; ++k) { const float prod = va[k] * (unit ? 1.0f : vb[k]); acc += prod; }
+        }
+        __syncthreads();
+    }
+    if (!consumer) return;
+    float A[36], nb[6], x[6];
+    {
+        int k = 0;
+        for (int a = 0; a < 6; ++a)
+            for (int b = a; b < 6; ++b) { const float val = __shfl_sync(0xffffffffu, acc, k++); A[a * 6 + b] = val; A[b * 6 + a] = val; }
+        for (int a = 0; a < 6; ++a) nb[a] = -__shfl_sync(0xffffffffu, acc, 21 + a);
+    }
+    const float total_error = __shfl_sync(0xffffffffu, acc, 27);
+    if (lane != 0) return;
+    st->n_corr_last = (int)n;
+    float delta[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) delta[i] = (i % 5 == 0) ? 1.0f : 0.0f;
+    ldlt6_solve(A, nb, x);                               // registration.cpp:366
+    Mat3 dR; euler_xyz_to_matrix(x[0], x[1], x[2], dR);  // registration.cpp:369-371
+    for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) delta[c * 4 + r] = dR(r, c); delta[12 + r] = x[3 + r]; }
     float Tn[16];
     mat4_mul(delta, st->T, Tn);
     const float prev_rmse = st->res_rmse;
@@ -806,7 +900,9 @@ int icp_run_impl(b3d_ctx* c, const float* T0, float thr, int max_iter, int p2pla
     const float4* src = c->src4.as<float4>();
     const bool binned = n_src >= 16384;
     const unsigned seq_tiles = (unsigned)div_up(n_src, kScanTile);
-    if (!plane && c->icp_mode != 1) {
+    const bool replay = plane ? c->icp_mode == 2 : c->icp_mode != 1;     // reference-order sequential sums
+    if (replay) {
+        if (plane) B3D_CUDA(c, c->seq_N.ensure(sizeof(float4) * n_src));
         B3D_CUDA(c, c->seq_rec.ensure(sizeof(float4) * n_src)); B3D_CUDA(c, c->seq_match.ensure(sizeof(uint32_t) * n_src));
         B3D_CUDA(c, c->seq_P.ensure(sizeof(float4) * n_src));   B3D_CUDA(c, c->seq_Q.ensure(sizeof(float4) * n_src));
         B3D_CUDA(c, c->scan_tmp.ensure(sizeof(unsigned) * (seq_tiles + 1)));
@@ -822,14 +918,14 @@ int icp_run_impl(b3d_ctx* c, const float* T0, float thr, int max_iter, int p2pla
         StageTimer timer(c, 5);
         const CellSlot* slots = c->grid_slots.as<CellSlot>();
         for (int iter = 0; iter < max_iter; ++iter) {
-            if (plane) {
+            if (plane && !replay) {
                 icp_accumulate_kernel<true><<<blocks, kIcpThreads, 0, c->stream>>>(src, n_src, st, thr, slots, c->grid_pts.as<float4>(),
                                                                                    c->fine_slots.as<CellSlot>(), c->fine_pts.as<float4>(),
                                                                                    c->tgt4.as<float4>(), c->nrm4.as<float4>(), gp, c->partials.as<double>());
                 B3D_LAUNCHED(c);
                 icp_update_kernel<true><<<1, kUpdateThreads, 0, c->stream>>>(c->partials.as<double>(), blocks, iter, (float)c->n_src, stop_on_conv, st);
                 B3D_LAUNCHED(c);
-            } else if (c->icp_mode != 1) {
+            } else if (replay) {
                 // reference-order sums: search -> ordered compaction -> sequential replay (see icp_seq_p2p_kernel)
                 if (binned) icp_search_kernel<true><<<blocks, kIcpThreads, 0, c->stream>>>(src, n_src, st, thr, slots, c->grid_pts.as<float4>(), c->fine_slots.as<CellSlot>(),
                                                                                            c->fine_pts.as<float4>(), gp, c->seq_rec.as<float4>(), c->seq_match.as<uint32_t>());
@@ -837,14 +933,16 @@ int icp_run_impl(b3d_ctx* c, const float* T0, float thr, int max_iter, int p2pla
                                                                                             c->fine_pts.as<float4>(), gp, c->seq_rec.as<float4>(), c->seq_match.as<uint32_t>());
                 B3D_LAUNCHED(c);
                 MatchFlag flag{c->seq_match.as<uint32_t>()};
-                CompactPairs emit{c->seq_rec.as<float4>(), c->seq_match.as<uint32_t>(), c->tgt4.as<float4>(), c->seq_P.as<float4>(), c->seq_Q.as<float4>()};
+                CompactPairs emit{c->seq_rec.as<float4>(), c->seq_match.as<uint32_t>(), c->tgt4.as<float4>(), c->seq_P.as<float4>(), c->seq_Q.as<float4>(),
+                                  plane ? c->nrm4.as<float4>() : nullptr, plane ? c->seq_N.as<float4>() : nullptr};
                 scan_tile_sums_kernel<<<seq_tiles, kScanThreads, 0, c->stream>>>(flag, n_src, c->scan_tmp.as<unsigned>());
                 B3D_LAUNCHED(c);
                 scan_tile_offsets_kernel<<<1, kScanThreads, 0, c->stream>>>(c->scan_tmp.as<unsigned>(), seq_tiles, &st->seq_count);
                 B3D_LAUNCHED(c);
                 scan_emit_kernel<<<seq_tiles, kScanThreads, 0, c->stream>>>(flag, emit, n_src, c->scan_tmp.as<unsigned>());
                 B3D_LAUNCHED(c);
-                icp_seq_p2p_kernel<<<1, kSeqThreads, 0, c->stream>>>(c->seq_P.as<float4>(), c->seq_Q.as<float4>(), &st->seq_count, iter, (float)c->n_src, stop_on_conv, st);
+                if (plane) icp_seq_plane_kernel<<<1, kSeqThreads, 0, c->stream>>>(c->seq_P.as<float4>(), c->seq_Q.as<float4>(), c->seq_N.as<float4>(), &st->seq_count, iter, (float)c->n_src, stop_on_conv, st);
+                else       icp_seq_p2p_kernel<<<1, kSeqThreads, 0, c->stream>>>(c->seq_P.as<float4>(), c->seq_Q.as<float4>(), &st->seq_count, iter, (float)c->n_src, stop_on_conv, st);
                 B3D_LAUNCHED(c);
             } else {
                 icp_accumulate_kernel<false><<<blocks, kIcpThreads, 0, c->stream>>>(src, n_src, st, thr, slots, c->grid_pts.as<float4>(),

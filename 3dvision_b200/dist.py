@@ -100,3 +100,28 @@ def sharded_ransac(backend, voxel_size: float, max_iterations: int, confidence: 
         keys = backend.reduce(h0, h1, with_limit=True)                   # best among ids <= exit id
         dist.all_reduce(keys[0:1], op=dist.ReduceOp.MAX, group=group)
     return backend.finish()
+
+
+def sharded_batch(instances, run_one, group=None, device="cpu"):
+    """Batched multi-object registration over `group` (SURVEY.md §8e, configs[3]): instance i is owned by
+    rank i mod G and processed there by `run_one(instance) -> (T 4x4, fitness, rmse)`; there is no
+    data-path collective.  The poses are then gathered with one SUM all-reduce of an (n,18) fp32 table
+    whose rows are zero everywhere but on the owner (disjoint rows, so SUM is a gather and the result is
+    bit-identical to the owner's).  `run_many`, if the callable has it, is used instead so a rank can
+    overlap its instances on its own worker pool.  Returns a list of (T, fitness, rmse), same on every rank."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    instances = list(instances)
+    n = len(instances)
+    mine = list(range(rank, n, world))
+    many = getattr(run_one, "run_many", None)
+    local = many([instances[i] for i in mine]) if many else [run_one(instances[i]) for i in mine]
+    table = np.zeros((n, 18), np.float32)
+    for i, (T, fit, rmse) in zip(mine, local):
+        table[i, :16] = np.asarray(T, np.float32).reshape(16)
+        table[i, 16], table[i, 17] = fit, rmse
+    t = torch.from_numpy(table).to(device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    table = t.cpu().numpy()
+    return [(table[i, :16].reshape(4, 4).copy(), float(table[i, 16]), float(table[i, 17])) for i in range(n)]

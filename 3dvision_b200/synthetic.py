@@ -126,6 +126,18 @@ def ransac_case(n_src=100_000, n_tgt=100_000, seed=1234 + 3, inlier_frac=0.7, vo
                       T_true.astype(np.float32), true_match, tnormals)
 
 
+def batch_cases(n_instances=64, seed=1234 + 4, n_src=30_000, n_tgt_lo=2_000, n_tgt_hi=10_000, max_iterations=100_000):
+    """configs[3]: `n_instances` object instances of the demo's scale (~30k scene points against a
+    2k-10k-point model), each with its own model sampling, pose, inlier fraction and seed."""
+    rng = np.random.default_rng(seed)
+    cases = []
+    for i in range(n_instances):
+        n_tgt = int(rng.integers(n_tgt_lo, n_tgt_hi + 1))
+        cases.append(ransac_case(n_src=n_src, n_tgt=n_tgt, seed=seed * 1000 + i, inlier_frac=float(rng.uniform(0.5, 0.8)),
+                                 voxel=0.002, noise=0.0004, max_iterations=max_iterations))
+    return cases
+
+
 def rotation_error(Ta, Tb) -> float:
     """Frobenius norm of the rotation-block difference (north_star tolerance: 1e-5)."""
     return float(np.linalg.norm(np.asarray(Ta, np.float64)[:3, :3] - np.asarray(Tb, np.float64)[:3, :3]))

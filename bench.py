@@ -273,6 +273,8 @@ def run_ours(args):
     ctx.set_clouds_device(d_src.data_ptr(), N_SRC, d_tgt.data_ptr(), None, N_TGT)
     ctx.set_features_device(d_sd.data_ptr(), d_td.data_ptr())
 
+    batched = batched_registration(b3d, bdist, syn, dev, rank, world, barrier, flush)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -314,8 +316,9 @@ def run_ours(args):
         "result": {"fitness": result[1], "rmse": result[2], "best_iteration": result[3]},
     }
 
+    line["also"] = {"batched": batched}
     if world == 1:
-        line["also"] = secondary(ctx, b3d, syn, case, flush)
+        line["also"].update(secondary(ctx, b3d, syn, case, flush))
         # same call with bail-out scoring (b3d_set_score_mode 3): identical winner / transform / fitness / rmse,
         # hypotheses that provably cannot reach the best full count are dropped part-way
         ctx.set_score_mode(3)
@@ -346,6 +349,46 @@ def run_ours(args):
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def batched_registration(b3d, bdist, syn, dev, rank, world, barrier, flush, n_instances=64, threads=8, reps=3):
+    """configs[3]: 64 object instances, each ransacRegistration(H=100000, conf 0.999) + icpRefine(<=200 it), dealt
+    round-robin to the ranks (instance i -> rank i mod N), each rank driving its share from a pool of `threads`
+    workers with one context/stream each — the reference's own unit of parallelism (pipeline.cpp:321-327).
+    Host buffers in, poses out; wall clock, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    pipe = importlib.import_module("3dvision_b200.pipeline")
+    reg = importlib.import_module("3dvision_b200.registration")
+    reg.Registration.device = dev
+    cases = syn.batch_cases(n_instances)
+    insts = [pipe.Instance(reg.PointCloud(c.source), reg.PointCloud(c.target, c.target_normals), reg.FPFHFeatures(c.source_desc),
+                           reg.FPFHFeatures(c.target_desc), c.voxel_size) for c in cases]
+
+    def run_one(inst):
+        _, f = pipe.process_instance(inst)
+        return f.transformation, f.fitness, f.rmse
+    run_one.run_many = lambda lst: [(f.transformation, f.fitness, f.rmse) for _, f in pipe.register_batch(lst, threads)]
+
+    out = bdist.sharded_batch(insts, run_one, device="cuda")            # warm-up: contexts, workspaces, RNG caches
+    secs = []
+    for _ in range(reps):
+        flush.zero_()
+        barrier()
+        t0 = time.perf_counter()
+        out = bdist.sharded_batch(insts, run_one, device="cuda")
+        torch.cuda.synchronize()
+        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        secs.append(float(t.item()))
+    s = float(np.median(secs))
+    return {"workload": f"configs[3]: {n_instances} instances (30k scene points vs 2k-10k model points each), ransacRegistration(H=100000, "
+                        f"conf 0.999) + icpRefine(thr 0.4*voxel, <=200 it), instance i -> rank i mod {world}, {threads} worker contexts per rank",
+            "registrations_per_s": n_instances / s, "ms_per_batch": 1e3 * s, "n_gpus": world,
+            "min_icp_fitness": float(min(o[1] for o in out)),
+            "max_rot_err_vs_truth": float(max(syn.rotation_error(o[0], c.T_true) for o, c in zip(out, cases))),
+            "max_trans_err_vs_truth": float(max(syn.translation_error(o[0], c.T_true) for o, c in zip(out, cases)))}
 
 
 def secondary(ctx, b3d, syn, case, flush):

@@ -149,7 +149,10 @@ int b3d_ransac_hypotheses(b3d_ctx* ctx, int h0, int h1, float* out_host /* 12 pe
  * as src/registration.cpp:341, 374-386 does (bit-identical sums; one sequential dependency chain per
  * sum, so large clouds cost ~5 cycles per matched point per pass); 1 = deterministic fp64 tree sums
  * (fast; differs from the reference by the reference's own rounding noise, ~1e-4 in the final pose).
- * Point-to-plane always uses the fp64 tree sums (it meets 1e-5 / 1e-6 m with them). */
+ * Point-to-plane uses the fp64 tree sums in modes 0 and 1 (they meet 1e-5 / 1e-6 m on well-conditioned
+ * problems); 2 = reference order for point-to-plane as well (src/registration.cpp:343-354: ATA, ATb and
+ * total_error added one matched point at a time) — bit-identical to the CPU path even where a threshold
+ * close to the noise floor makes the iteration sensitive to the last bit of the sums. */
 int b3d_set_icp_mode(b3d_ctx* ctx, int mode);
 /* ICP on resident clouds. stop_on_convergence = 0 disables the |d rmse| < 1e-6 break
  * (src/registration.cpp:406) for fixed-iteration throughput runs. */

@@ -117,3 +117,32 @@ def test_key_packing_orders_like_the_sequential_rule():
     assert bdist.unpack_best_key(k(0.7001799941062927, 21264)) == (float(np.float32(0.7001799941062927)), 21264)
     assert bdist.unpack_best_key(0) == (0.0, -1)
     assert bdist.pack_exit_key(5) > bdist.pack_exit_key(9)          # MAX picks the earliest exit
+
+
+def _batch_worker(rank, world, port, n_inst):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import oracle as O
+        cases = [syn.ransac_case(n_src=300, n_tgt=200 + 10 * i, seed=50 + i, max_iterations=200) for i in range(n_inst)]
+        seen = []
+
+        def run_one(c):
+            seen.append(c)
+            r = O.ransac_registration(c.source, c.target, c.source_desc, c.target_desc, c.voxel_size, 200, 0.999)
+            f = O.icp(c.source, c.target, c.target_normals, r.transformation, c.voxel_size * 0.4, 5, True)
+            return f.transformation, f.fitness, f.rmse
+
+        out = bdist.sharded_batch(cases, run_one)
+        assert len(seen) == len(range(rank, n_inst, world))                 # instance i -> rank i mod G, nothing else
+        assert all(c is cases[i] for c, i in zip(seen, range(rank, n_inst, world)))
+        for c, (T, fit, rmse) in zip(cases, out):                           # every rank ends with every pose, bit-identical
+            T1, f1, r1 = run_one(c)
+            assert np.array_equal(T, T1) and np.float32(fit) == np.float32(f1) and np.float32(rmse) == np.float32(r1)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_inst", [5, 1, 0])      # odd count, fewer instances than ranks, empty batch
+def test_sharded_batch_deals_instances_round_robin_and_gathers_poses(n_inst):
+    mp.spawn(_batch_worker, args=(2, _free_port(), n_inst), nprocs=2, join=True)

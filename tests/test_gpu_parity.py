@@ -222,6 +222,37 @@ def test_icp_point_to_point_is_bit_identical(ctx, oracle, iters):
     assert np.array_equal(T, ref.transformation) and fit == ref.fitness and rmse == ref.rmse
 
 
+@pytest.mark.parametrize("iters", [1, 2, 7, 40])
+def test_icp_point_to_plane_reference_order_is_bit_identical(ctx, oracle, iters):
+    """b3d_set_icp_mode(2): ATA / ATb / total_error added one matched point at a time (registration.cpp:343-354)."""
+    case = icp_small()
+    ref = oracle.icp(case.source, case.target, case.target_normals, case.T_init, case.threshold, iters, True)
+    ctx.set_icp_mode(2)
+    try:
+        T, fit, rmse, n = ctx.icp(case.source, case.target, case.target_normals, case.T_init, case.threshold, iters, True)
+    finally:
+        ctx.set_icp_mode(0)
+    assert n == ref.extra["iters_run"]
+    assert np.array_equal(T, ref.transformation) and np.float32(fit) == np.float32(ref.fitness) and np.float32(rmse) == np.float32(ref.rmse)
+
+
+def test_icp_point_to_plane_reference_order_threshold_at_the_noise_floor(ctx, oracle):
+    """Threshold 0.4*voxel ~ sensor noise (the orchestrator's default, pipeline.cpp:104): few matches, the matched set
+    flips with the last bit of the pose, and only the reference's own summation order reproduces its result exactly.
+    Also the binned (n_src >= 16384) query order."""
+    for n_src, n_tgt, seed in ((2977, 1842, 94), (20000, 3000, 95)):
+        c = syn.ransac_case(n_src=n_src, n_tgt=n_tgt, seed=seed, max_iterations=10)
+        T0 = c.T_true.copy(); T0[:3, 3] += np.float32(2e-4)
+        ref = oracle.icp(c.source, c.target, c.target_normals, T0, c.voxel_size * 0.4, 30, True)
+        ctx.set_icp_mode(2)
+        try:
+            T, fit, rmse, n = ctx.icp(c.source, c.target, c.target_normals, T0, c.voxel_size * 0.4, 30, True)
+        finally:
+            ctx.set_icp_mode(0)
+        assert n == ref.extra["iters_run"] and np.array_equal(T, ref.transformation)
+        assert np.float32(fit) == np.float32(ref.fitness) and np.float32(rmse) == np.float32(ref.rmse)
+
+
 def test_icp_point_to_point_large_binned_source_is_bit_identical(ctx, oracle):
     """n_src >= 16384 takes the cell-binned query order; results are still written and summed in source order."""
     case = syn.icp_case(n_model=3000, n_scene=20000, seed=61)
