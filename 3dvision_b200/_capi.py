@@ -31,6 +31,7 @@ SYMBOLS = [
     "b3d_correspondences_devptr", "b3d_set_score_mode", "b3d_ransac_prepare", "b3d_ransac_score", "b3d_ransac_reduce", "b3d_ransac_finish",
     "b3d_ransac_counts", "b3d_ransac_hypotheses", "b3d_set_icp_mode", "b3d_icp_run", "b3d_icp_nearest",
     "b3d_kernel_launches", "b3d_stage_ms", "b3d_measure_fp32_rate", "b3d_score_recounts",
+    "b3d_voxel_downsample", "b3d_estimate_normals", "b3d_compute_fpfh",
 ]
 
 
@@ -99,6 +100,9 @@ def _declare(L):
     L.b3d_stage_ms.restype = C.c_float
     L.b3d_measure_fp32_rate.argtypes = [_vp, C.POINTER(C.c_double)]
     L.b3d_score_recounts.argtypes = [_vp, C.POINTER(C.c_uint64)]
+    L.b3d_voxel_downsample.argtypes = [_vp, _vp, C.c_size_t, _vp, C.c_float, _vp, _vp, C.c_size_t, C.POINTER(C.c_size_t)]
+    L.b3d_estimate_normals.argtypes = [_vp, _vp, C.c_size_t, C.c_int, _vp]
+    L.b3d_compute_fpfh.argtypes = [_vp, _vp, _vp, C.c_size_t, C.c_float, _vp]
 
 
 def cuda_available() -> bool:
@@ -305,6 +309,32 @@ class Context:
                                         int(bool(point_to_plane)), int(bool(stop_on_convergence)),
                                         T.ctypes.data_as(_f32p), C.byref(fit), C.byref(rm), C.byref(it)))
         return _T_from_colmajor(T), fit.value, rm.value, it.value
+
+    # ---- stages feeding the hot path (registration.cpp:29-60, 105-130, 133-201)
+    def voxel_downsample(self, xyz, voxel_size, colors=None):
+        xyz = _as_f32(xyz, 3)
+        n = xyz.shape[0]
+        col = _as_f32(colors, 3) if colors is not None and np.asarray(colors).size else None
+        out = np.empty((max(n, 1), 3), np.float32)
+        out_col = np.empty((max(n, 1), 3), np.float32) if col is not None else None
+        m = C.c_size_t()
+        self._check(self._L.b3d_voxel_downsample(self._h, _ptr(xyz), n, _ptr(col) if col is not None else None, voxel_size,
+                                                 _ptr(out), _ptr(out_col) if out_col is not None else None, n, C.byref(m)))
+        return out[:m.value].copy(), (out_col[:m.value].copy() if out_col is not None else None)
+
+    def estimate_normals(self, xyz, k=30):
+        xyz = _as_f32(xyz, 3)
+        out = np.empty_like(xyz)
+        self._check(self._L.b3d_estimate_normals(self._h, _ptr(xyz), xyz.shape[0], int(k), _ptr(out)))
+        return out
+
+    def compute_fpfh(self, xyz, normals, radius):
+        xyz = _as_f32(xyz, 3); nrm = _as_f32(normals, 3)
+        if nrm.shape[0] != xyz.shape[0]:
+            raise ValueError("compute_fpfh: one normal per point required")
+        out = np.empty((xyz.shape[0], 33), np.float32)
+        self._check(self._L.b3d_compute_fpfh(self._h, _ptr(xyz), _ptr(nrm), xyz.shape[0], radius, _ptr(out)))
+        return out
 
     def icp_nearest(self, T, distance_threshold):
         Tc = _T_colmajor(T)

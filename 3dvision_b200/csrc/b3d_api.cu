@@ -112,6 +112,7 @@ void b3d_ctx_destroy(b3d_ctx* c) {
                       &c->seq_rec, &c->seq_match, &c->seq_P, &c->seq_Q, &c->seq_N, &c->fine_slots, &c->fine_pts, &c->bail_list_a, &c->bail_list_b, &c->bail_state, &c->src_slots, &c->src_sorted, &c->src_slot, &c->src_rank,
                       &c->tc_a_tiles, &c->tc_b_tiles, &c->tc_norm2, &c->tc_best, &c->tc_aux};
     for (DevBuf* b : bufs) b->release();
+    for (DevBuf& b : c->fbuf) b.release();
     if (c->h_state) cudaFreeHost(c->h_state);
     for (int s = 0; s < kStages; ++s) { if (c->ev_start[s]) cudaEventDestroy(c->ev_start[s]); if (c->ev_stop[s]) cudaEventDestroy(c->ev_stop[s]); }
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -208,6 +209,25 @@ int b3d_score_recounts(b3d_ctx* c, uint64_t* out) {
     B3D_CUDA(c, cudaStreamSynchronize(c->stream));
     *out = v;
     return B3D_OK;
+}
+
+int b3d_voxel_downsample(b3d_ctx* c, const float* xyz, size_t n, const float* colors_or_null, float voxel_size,
+                         float* out_xyz, float* out_colors_or_null, size_t capacity, size_t* out_n) {
+    if (!c || !out_n || (n && (!xyz || !out_xyz))) return B3D_ERR_INVALID;
+    B3D_CUDA(c, cudaSetDevice(c->device));
+    return voxel_downsample_impl(c, xyz, n, colors_or_null, voxel_size, out_xyz, out_colors_or_null, capacity, out_n);
+}
+
+int b3d_estimate_normals(b3d_ctx* c, const float* xyz, size_t n, int k, float* out_normals) {
+    if (!c || (n && (!xyz || !out_normals))) return B3D_ERR_INVALID;
+    B3D_CUDA(c, cudaSetDevice(c->device));
+    return estimate_normals_impl(c, xyz, n, k, out_normals);
+}
+
+int b3d_compute_fpfh(b3d_ctx* c, const float* xyz, const float* normals, size_t n, float radius, float* out_desc) {
+    if (!c || (n && (!xyz || !normals || !out_desc))) return B3D_ERR_INVALID;
+    B3D_CUDA(c, cudaSetDevice(c->device));
+    return compute_fpfh_impl(c, xyz, normals, n, radius, out_desc);
 }
 
 int b3d_set_icp_mode(b3d_ctx* c, int mode) {

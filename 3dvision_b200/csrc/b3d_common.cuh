@@ -13,7 +13,7 @@ namespace b3d {
 
 constexpr int kNumSMs = 148;          // B200: 2 dies x 74 SMs; grids are sized in multiples of this
 constexpr int kDescDim = B3D_DESC_DIM;
-constexpr int kStages = 7;
+constexpr int kStages = 10;
 
 struct DevBuf {
     void* p = nullptr;
@@ -100,6 +100,9 @@ struct b3d_ctx {
     int icp_mode = 0;                                        // 0: point-to-point adds in the reference's order; 1: fp64 tree sums everywhere; 2: reference order for plane too                        // second-level (finer) target grid
     b3d::DevBuf src_slots, src_sorted, src_slot, src_rank;   // source reordered by target cell (coherent warps)
 
+    // feature stages (b3d_features.cu): scratch pool, slots named there
+    b3d::DevBuf fbuf[32];
+
     // device scalars + pinned host mirror
     b3d::DevBuf state;                       // b3d::DeviceState
     b3d::DeviceState* h_state = nullptr;     // pinned
@@ -151,5 +154,9 @@ int icp_run_impl(b3d_ctx* c, const float* T0, float thr, int max_iter, int p2pla
                  float* T, float* fitness, float* rmse, int32_t* iters);
 int icp_nearest_impl(b3d_ctx* c, const float* T, float thr, uint32_t* idx_host, float* d2_host);
 int xyz_to_float4(b3d_ctx* c, const float* xyz_dev, size_t n, float4* out);
+int voxel_downsample_impl(b3d_ctx* c, const float* xyz, size_t n, const float* colors, float voxel, float* out_xyz, float* out_colors,
+                          size_t capacity, size_t* out_n);
+int estimate_normals_impl(b3d_ctx* c, const float* xyz, size_t n, int k, float* out_normals);
+int compute_fpfh_impl(b3d_ctx* c, const float* xyz, const float* normals, size_t n, float radius, float* out_desc);
 
 }  // namespace b3d

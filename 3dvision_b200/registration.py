@@ -8,9 +8,8 @@ stojicnnnn/3DVision, so a caller of ``Registration::ransacRegistration`` /
 Python face used by the tests and bench).  All compute happens in libb3d.so
 through the C-ABI of ``include/b3d.h``; nothing here computes on the CPU.
 
-Only the hot-path members are provided: ``voxelDownsample``, ``estimateNormals``,
-``computeFPFH`` and ``loadReferenceModel`` are outside the round-1 scope
- and are deliberately absent.
+``voxelDownsample``, ``estimateNormals`` and ``computeFPFH`` are
+provided too; ``loadReferenceModel`` (file I/O) is out of scope and absent.
 """
 from __future__ import annotations
 
@@ -77,6 +76,24 @@ class Registration:
     """Static interface of registration.hpp:32-60 (hot-path members only)."""
 
     device = 0
+
+    @staticmethod
+    def voxelDownsample(cloud: PointCloud, voxel_size: float) -> PointCloud:
+        """registration.hpp:34 / registration.cpp:29-60. Points (and colors) averaged per voxel, emitted in the
+        reference's unordered_map iteration order; normals are dropped, as there."""
+        pts, col = _context(Registration.device).voxel_downsample(cloud.points, float(voxel_size),
+                                                                  cloud.colors if cloud.hasColors() and cloud.size() else None)
+        return PointCloud(points=pts, colors=col if col is not None else np.zeros((0, 3), np.float32))
+
+    @staticmethod
+    def estimateNormals(cloud: PointCloud, k: int = 30) -> None:
+        """registration.hpp:36 / registration.cpp:105-130. In place, like the reference."""
+        cloud.normals = _context(Registration.device).estimate_normals(cloud.points, int(k))
+
+    @staticmethod
+    def computeFPFH(cloud: PointCloud, radius: float) -> FPFHFeatures:
+        """registration.hpp:38 / registration.cpp:133-201."""
+        return FPFHFeatures(_context(Registration.device).compute_fpfh(cloud.points, cloud.normals, float(radius)))
 
     @staticmethod
     def ransacRegistration(source: PointCloud, target: PointCloud,

@@ -145,6 +145,25 @@ int b3d_ransac_finish(b3d_ctx* ctx, const int64_t* keys_dev,
 int b3d_ransac_counts(b3d_ctx* ctx, int h0, int h1, int32_t* out_host);
 int b3d_ransac_hypotheses(b3d_ctx* ctx, int h0, int h1, float* out_host /* 12 per hypothesis */);
 
+/* ---- stages that feed the hot path; host buffers in and out ------------
+ * Replaces Registration::voxelDownsample (include/registration.hpp:34, src/registration.cpp:29-60).
+ * One output point per occupied voxel floor(p / voxel): the mean of its members added in input order,
+ * emitted in the iteration order of the reference's std::unordered_map (same libstdc++ container, same
+ * hash), because later stages index into this order.  colors_or_null / out_colors_or_null: averaged the
+ * same way when given (normals are dropped, as in the reference).  *out_n = number of voxels; if it
+ * exceeds `capacity` nothing is written and B3D_ERR_INVALID is returned (n is always enough). */
+int b3d_voxel_downsample(b3d_ctx* ctx, const float* xyz, size_t n, const float* colors_or_null, float voxel_size,
+                         float* out_xyz, float* out_colors_or_null, size_t capacity, size_t* out_n);
+/* Replaces Registration::estimateNormals (registration.hpp:36, src/registration.cpp:63-81, 105-130):
+ * k nearest (self included) ordered by (d2, index), centroid and covariance summed in that order,
+ * eigenvector of the smallest eigenvalue (Eigen SelfAdjointEigenSolver, iterative), flipped towards the
+ * origin.  1 <= k <= 128. */
+int b3d_estimate_normals(b3d_ctx* ctx, const float* xyz, size_t n, int k, float* out_normals);
+/* Replaces Registration::computeFPFH (registration.hpp:38, src/registration.cpp:83-102, 133-201):
+ * neighbours with d2 <= radius^2, the 100 first by (d2, index); SPFH bins; 1/dist-weighted sum in list
+ * order; L1 normalisation.  out_desc is n x 33. */
+int b3d_compute_fpfh(b3d_ctx* ctx, const float* xyz, const float* normals, size_t n, float radius, float* out_desc);
+
 /* Point-to-point accumulation: 0 (default) = add the matched pairs in source order in fp32, exactly
  * as src/registration.cpp:341, 374-386 does (bit-identical sums; one sequential dependency chain per
  * sum, so large clouds cost ~5 cycles per matched point per pass); 1 = deterministic fp64 tree sums
