@@ -218,6 +218,12 @@ int b3d_voxel_downsample(b3d_ctx* c, const float* xyz, size_t n, const float* co
     return voxel_downsample_impl(c, xyz, n, colors_or_null, voxel_size, out_xyz, out_colors_or_null, capacity, out_n);
 }
 
+int b3d_set_voxel_order_mode(b3d_ctx* c, int mode) {
+    if (!c || mode < 0 || mode > 1) return B3D_ERR_INVALID;
+    c->voxel_order_mode = mode;
+    return B3D_OK;
+}
+
 int b3d_estimate_normals(b3d_ctx* c, const float* xyz, size_t n, int k, float* out_normals) {
     if (!c || (n && (!xyz || !out_normals))) return B3D_ERR_INVALID;
     B3D_CUDA(c, cudaSetDevice(c->device));

@@ -102,6 +102,7 @@ struct b3d_ctx {
 
     // feature stages (b3d_features.cu): scratch pool, slots named there
     b3d::DevBuf fbuf[32];
+    int voxel_order_mode = 0;                // 0: container order simulated on the device; 1: real std::unordered_map on the host
 
     // device scalars + pinned host mirror
     b3d::DevBuf state;                       // b3d::DeviceState

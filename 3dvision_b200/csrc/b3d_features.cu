@@ -33,7 +33,7 @@ namespace b3d {
 
 // fbuf slots
 enum { F_PTS4 = 0, F_NRM4, F_SLOTS, F_GP, F_SORTED, F_PT_SLOT, F_PT_RANK, F_COV, F_OUT, F_NBR, F_NBR_CNT, F_SPFH,
-       F_KEYS_A, F_KEYS_B, F_IDX_A, F_IDX_B, F_CUB, F_SEG, F_VOX_MEAN, F_VOX_COL, F_VOX_KEY, F_VOX_FIRST, F_VOX_ORDER, F_PERM, F_RAW, F_RAW2 };
+       F_KEYS_A, F_KEYS_B, F_IDX_A, F_IDX_B, F_CUB, F_SEG, F_VOX_MEAN, F_VOX_COL, F_VOX_KEY, F_VOX_FIRST, F_VOX_ORDER, F_PERM, F_RAW, F_RAW2, F_ORD_OPEN, F_ORD_KEYS, F_ORD_SEQ };
 
 constexpr int kFeatWarps = 8;                 // warps (= queries in flight) per block
 constexpr int kKeyBuf = 256;                  // per-warp key buffer: sorted prefix + staged candidates
@@ -416,6 +416,87 @@ struct VoxKeyHash {
     }
 };
 
+// ---- iteration order of libstdc++'s unordered_map, computed on the device --------------------------------------
+// A node enters the container's singly linked list either right behind the "before" node of its bucket (bucket
+// already in use: it becomes the first node of that bucket's run) or at the global head (bucket empty).  A rehash
+// re-inserts every node, in current list order, by the same rule into the new bucket array.  So after a rehash to
+// B buckets at element count n_p, the list is what inserting S = (list order before the rehash) ++ (the elements that
+// arrive until the next rehash) into an empty B-bucket table gives, and that is: runs ordered by the time their
+// bucket was first used, latest first; inside a run, latest first — i.e. S sorted descending by (first-use time of
+// the element's bucket, own time).  The rehash points and bucket counts come from libstdc++'s own
+// _Prime_rehash_policy object (the one unordered_map uses), so growth matches whatever libstdc++ is linked.
+struct RehashStep { unsigned at; unsigned buckets; };
+
+static void rehash_schedule(unsigned m, std::vector<RehashStep>& out) {
+    std::__detail::_Prime_rehash_policy policy;                                     // max_load_factor 1.0, like the reference's map
+    size_t buckets = 1, count = 0;                                                  // a default-constructed map has one bucket
+    while (count < m) {
+        const std::pair<bool, size_t> r = policy._M_need_rehash(buckets, count, 1);
+        if (r.first) { buckets = r.second; out.push_back({(unsigned)count, (unsigned)buckets}); }
+        const size_t quiet_until = policy._M_next_resize;                           // no decision changes while count + 1 <= this
+        count = quiet_until > count + 1 ? quiet_until : count + 1;
+    }
+}
+
+__device__ __forceinline__ unsigned long long voxel_hash(int x, int y, int z) {     // registration.cpp:20-26; std::hash<int> is the identity
+    unsigned long long h = (unsigned long long)(long long)x;
+    h ^= (unsigned long long)(long long)y + 0x9e3779b9ull + (h << 6) + (h >> 2);
+    h ^= (unsigned long long)(long long)z + 0x9e3779b9ull + (h << 6) + (h >> 2);
+    return h;
+}
+
+__global__ void order_open_kernel(const unsigned* __restrict__ seq_prev, unsigned n_prev, unsigned n_now, const int* __restrict__ key3,
+                                  unsigned buckets, unsigned* __restrict__ open, unsigned* __restrict__ bucket_of, unsigned* __restrict__ elem) {
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_now) return;
+    const unsigned r = t < n_prev ? seq_prev[t] : t;                                // new arrivals come in first-appearance order
+    const unsigned b = (unsigned)(voxel_hash(key3[3 * (size_t)r], key3[3 * (size_t)r + 1], key3[3 * (size_t)r + 2]) % buckets);
+    atomicMin(&open[b], t);
+    bucket_of[t] = b; elem[t] = r;
+}
+
+__global__ void order_key_kernel(const unsigned* __restrict__ open, const unsigned* __restrict__ bucket_of, unsigned n_now, int bits,
+                                 unsigned long long* __restrict__ keys) {
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_now) return;
+    keys[t] = ((unsigned long long)open[bucket_of[t]] << bits) | t;
+}
+
+// perm[pos] = first-appearance rank of the voxel the reference emits at position pos
+static int container_order_device(b3d_ctx* c, const int* key3_ordered, unsigned m, unsigned* perm) {
+    std::vector<RehashStep> steps;
+    rehash_schedule(m, steps);
+    const unsigned max_buckets = steps.empty() ? 1u : steps.back().buckets;
+    B3D_CUDA(c, c->fbuf[F_ORD_OPEN].ensure(sizeof(unsigned) * ((size_t)max_buckets + 2 * (size_t)m)));
+    B3D_CUDA(c, c->fbuf[F_ORD_KEYS].ensure(sizeof(unsigned long long) * 2 * (size_t)m));
+    B3D_CUDA(c, c->fbuf[F_ORD_SEQ].ensure(sizeof(unsigned) * 2 * (size_t)m));
+    unsigned* open = c->fbuf[F_ORD_OPEN].as<unsigned>();
+    unsigned* bucket_of = open + max_buckets; unsigned* elem = bucket_of + m;
+    unsigned long long* keys_in = c->fbuf[F_ORD_KEYS].as<unsigned long long>(); unsigned long long* keys_out = keys_in + m;
+    unsigned* seq[2] = {c->fbuf[F_ORD_SEQ].as<unsigned>(), c->fbuf[F_ORD_SEQ].as<unsigned>() + m};
+    int cur = 0;
+    unsigned n_prev = 0;
+    for (size_t p = 0; p < steps.size(); ++p) {
+        const unsigned n_now = p + 1 < steps.size() ? steps[p + 1].at : m;          // elements present when the next rehash (or the end) comes
+        const unsigned buckets = steps[p].buckets;
+        int bits = 1; while ((1ull << bits) < (unsigned long long)n_now + 1ull) ++bits;
+        B3D_CUDA(c, cudaMemsetAsync(open, 0xFF, sizeof(unsigned) * buckets, c->stream));
+        order_open_kernel<<<div_up(n_now, 256), 256, 0, c->stream>>>(seq[cur], n_prev, n_now, key3_ordered, buckets, open, bucket_of, elem);
+        B3D_LAUNCHED(c);
+        order_key_kernel<<<div_up(n_now, 256), 256, 0, c->stream>>>(open, bucket_of, n_now, bits, keys_in);
+        B3D_LAUNCHED(c);
+        unsigned* dst = (p + 1 == steps.size()) ? perm : seq[cur ^ 1];
+        size_t tmp_bytes = 0;
+        B3D_CUDA(c, cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp_bytes, keys_in, keys_out, elem, dst, (int)n_now, 0, 2 * bits, c->stream));
+        B3D_CUDA(c, c->fbuf[F_CUB].ensure(tmp_bytes + 16));
+        B3D_CUDA(c, cub::DeviceRadixSort::SortPairsDescending(c->fbuf[F_CUB].p, tmp_bytes, keys_in, keys_out, elem, dst, (int)n_now, 0, 2 * bits, c->stream));
+        c->launches += 3;
+        cur ^= 1;
+        n_prev = n_now;
+    }
+    return B3D_OK;
+}
+
 // ---------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------
@@ -622,16 +703,22 @@ int voxel_downsample_impl(b3d_ctx* c, const float* xyz, size_t n_, const float* 
     c->launches += 4;
     gather_keys_kernel<<<div_up(m, 256), 256, 0, c->stream>>>(key3, order, m, key3_ordered);
     B3D_LAUNCHED(c);
-    std::vector<int> h_keys(3 * (size_t)m);
-    B3D_CUDA(c, cudaMemcpyAsync(h_keys.data(), key3_ordered, sizeof(int) * 3 * m, cudaMemcpyDeviceToHost, c->stream));
-    B3D_CUDA(c, cudaStreamSynchronize(c->stream));
-    std::vector<unsigned> perm; perm.reserve(m);
-    {
-        std::unordered_map<VoxKey, unsigned, VoxKeyHash> grid;                      // no reserve(): the reference does not either
-        for (unsigned r = 0; r < m; ++r) grid.emplace(VoxKey{h_keys[3 * (size_t)r], h_keys[3 * (size_t)r + 1], h_keys[3 * (size_t)r + 2]}, r);
-        for (const auto& kv : grid) perm.push_back(kv.second);
+    if (c->voxel_order_mode == 1) {                                                 // cross-check path: the real container on the host
+        std::vector<int> h_keys(3 * (size_t)m);
+        B3D_CUDA(c, cudaMemcpyAsync(h_keys.data(), key3_ordered, sizeof(int) * 3 * m, cudaMemcpyDeviceToHost, c->stream));
+        B3D_CUDA(c, cudaStreamSynchronize(c->stream));
+        std::vector<unsigned> perm; perm.reserve(m);
+        {
+            std::unordered_map<VoxKey, unsigned, VoxKeyHash> grid;                  // no reserve(): the reference does not either
+            for (unsigned r = 0; r < m; ++r) grid.emplace(VoxKey{h_keys[3 * (size_t)r], h_keys[3 * (size_t)r + 1], h_keys[3 * (size_t)r + 2]}, r);
+            for (const auto& kv : grid) perm.push_back(kv.second);
+        }
+        B3D_CUDA(c, cudaMemcpyAsync(c->fbuf[F_PERM].p, perm.data(), sizeof(unsigned) * m, cudaMemcpyHostToDevice, c->stream));
+        B3D_CUDA(c, cudaStreamSynchronize(c->stream));                              // perm is a local
+    } else {
+        int rc = container_order_device(c, key3_ordered, m, c->fbuf[F_PERM].as<unsigned>());
+        if (rc != B3D_OK) return rc;
     }
-    B3D_CUDA(c, cudaMemcpyAsync(c->fbuf[F_PERM].p, perm.data(), sizeof(unsigned) * m, cudaMemcpyHostToDevice, c->stream));
     float* d_out = c->fbuf[F_OUT].as<float>(); float* d_out_col = colors ? d_out + 3 * (size_t)m : nullptr;
     gather_voxels_kernel<<<div_up(m, 256), 256, 0, c->stream>>>(mean, mean_col, order, c->fbuf[F_PERM].as<unsigned>(), m, d_out, d_out_col);
     B3D_LAUNCHED(c);

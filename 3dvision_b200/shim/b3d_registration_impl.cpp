@@ -4,6 +4,7 @@
 //   Registration::icpRefine            src/registration.cpp:297-414
 //   GPURegistration::icpRefine         src/gpu_impl.cpp:141-260
 //   GPURegistration::isCudaAvailable   src/gpu_impl.cpp
+//   (with -DB3D_SHIM_FEATURE_STAGES) Registration::voxelDownsample / estimateNormals / computeFPFH
 // (see INTEGRATION.md for the three-line patch to the reference's CMakeLists.txt / sources).
 // B3D_REFERENCE_HEADERS lets a test substitute declarations for the reference's headers.
 #ifdef B3D_REFERENCE_HEADERS
@@ -33,5 +34,13 @@ RegistrationResult GPURegistration::icpRefine(const PointCloud& source, const Po
 }
 
 bool GPURegistration::isCudaAvailable() { return b3d_shim::isCudaAvailable(); }
+
+// The stages that feed the hot path.  Define B3D_SHIM_FEATURE_STAGES when the reference's own bodies
+// (src/registration.cpp:29-60, 105-130, 133-201) are removed as well; otherwise they stay the reference's.
+#ifdef B3D_SHIM_FEATURE_STAGES
+PointCloud Registration::voxelDownsample(const PointCloud& cloud, float voxel_size) { return b3d_shim::voxelDownsample(cloud, voxel_size); }
+void Registration::estimateNormals(PointCloud& cloud, int k) { b3d_shim::estimateNormals(cloud, k); }
+FPFHFeatures Registration::computeFPFH(const PointCloud& cloud, float radius) { return b3d_shim::computeFPFH(cloud, radius); }
+#endif
 
 }  // namespace industry_picking

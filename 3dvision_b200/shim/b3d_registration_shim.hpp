@@ -10,6 +10,7 @@
 //   Registration::icpRefine               (registration.hpp:50-57)
 //   GPURegistration::icpRefine            (gpu_registration.hpp:10-16)
 //   GPURegistration::isCudaAvailable      (gpu_registration.hpp:18)
+//   Registration::voxelDownsample / estimateNormals / computeFPFH   (registration.hpp:34-38)
 // implemented over the C-ABI of b3d.h (libb3d.so, sm_100a CUDA kernels).  b3d_registration_impl.cpp
 // turns them into the out-of-line definitions of the reference's static member functions.
 //
@@ -88,6 +89,40 @@ inline RegistrationResult icpRefine(const PointCloud& source, const PointCloud& 
 }
 
 inline bool isCudaAvailable() { return b3d_cuda_available() != 0; }
+
+// ---- stages that feed the hot path (registration.hpp:34-38; src/registration.cpp:29-60, 105-130, 133-201) ----
+inline float* xyz(std::vector<Eigen::Vector3f>& v) { return v.empty() ? nullptr : reinterpret_cast<float*>(v.data()); }
+
+inline PointCloud voxelDownsample(const PointCloud& cloud, float voxel_size) {
+    b3d_ctx* ctx = context();
+    PointCloud result;
+    const size_t n = cloud.points.size();
+    const bool colors = cloud.colors.size() == n && n > 0;                       // PointCloud::hasColors()
+    result.points.resize(n);
+    if (colors) result.colors.resize(n);
+    size_t m = 0;
+    check(ctx, b3d_voxel_downsample(ctx, xyz(cloud.points), n, colors ? xyz(cloud.colors) : nullptr, voxel_size,
+                                    xyz(result.points), colors ? xyz(result.colors) : nullptr, n, &m));
+    result.points.resize(m);
+    if (colors) result.colors.resize(m);
+    return result;                                                              // normals are dropped, as in the reference
+}
+
+inline void estimateNormals(PointCloud& cloud, int k = 30) {
+    b3d_ctx* ctx = context();
+    cloud.normals.resize(cloud.points.size());
+    check(ctx, b3d_estimate_normals(ctx, xyz(cloud.points), cloud.points.size(), k, xyz(cloud.normals)));
+}
+
+inline FPFHFeatures computeFPFH(const PointCloud& cloud, float radius) {
+    if (cloud.normals.size() != cloud.points.size()) throw std::runtime_error("b3d: computeFPFH needs one normal per point");
+    b3d_ctx* ctx = context();
+    FPFHFeatures features;
+    features.descriptors.resize(cloud.points.size());
+    check(ctx, b3d_compute_fpfh(ctx, xyz(cloud.points), xyz(cloud.normals), cloud.points.size(), radius,
+                                features.descriptors.empty() ? nullptr : features.descriptors.data()->data()));
+    return features;
+}
 
 // GPURegistration::icpRefine has no point_to_plane argument; the reference GPU path is always
 // point-to-plane (src/gpu_impl.cpp:141-260).  Parity target is the CPU semantics.

@@ -154,6 +154,10 @@ int b3d_ransac_hypotheses(b3d_ctx* ctx, int h0, int h1, float* out_host /* 12 pe
  * exceeds `capacity` nothing is written and B3D_ERR_INVALID is returned (n is always enough). */
 int b3d_voxel_downsample(b3d_ctx* ctx, const float* xyz, size_t n, const float* colors_or_null, float voxel_size,
                          float* out_xyz, float* out_colors_or_null, size_t capacity, size_t* out_n);
+/* How the output order is obtained: 0 (default) = the container's insertion / rehash rules replayed on the
+ * device (per-rehash radix sorts; growth schedule taken from libstdc++'s own _Prime_rehash_policy);
+ * 1 = the distinct keys are pushed through a real std::unordered_map on the host (slow, cross-check). */
+int b3d_set_voxel_order_mode(b3d_ctx* ctx, int mode);
 /* Replaces Registration::estimateNormals (registration.hpp:36, src/registration.cpp:63-81, 105-130):
  * k nearest (self included) ordered by (d2, index), centroid and covariance summed in that order,
  * eigenvector of the smallest eigenvalue (Eigen SelfAdjointEigenSolver, iterative), flipped towards the

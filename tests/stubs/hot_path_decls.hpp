@@ -16,6 +16,9 @@ struct FPFHFeatures { std::vector<std::array<float, 33>> descriptors; };
 struct RegistrationResult { Eigen::Matrix4f transformation = Eigen::Matrix4f::Identity(); float fitness = 0.0f; float rmse = 0.0f; };
 class Registration {
 public:
+    static PointCloud voxelDownsample(const PointCloud& cloud, float voxel_size);
+    static void estimateNormals(PointCloud& cloud, int k = 30);
+    static FPFHFeatures computeFPFH(const PointCloud& cloud, float radius);
     static RegistrationResult ransacRegistration(const PointCloud&, const PointCloud&, const FPFHFeatures&, const FPFHFeatures&,
                                                  float voxel_size, int max_iterations = 100000, float confidence = 0.999f);
     static RegistrationResult icpRefine(const PointCloud&, const PointCloud&, const Eigen::Matrix4f&, float distance_threshold,

@@ -18,7 +18,7 @@ syn = importlib.import_module("3dvision_b200.synthetic")
 
 def build_driver(tmp_path, use_reference_headers: bool):
     exe = str(tmp_path / ("shim_driver_ref" if use_reference_headers else "shim_driver"))
-    cmd = ["g++", "-std=c++17", "-O1", "-Wall", f"-I{STUBS}", f"-I{SHIM}", f"-I{ROOT}/include"]
+    cmd = ["g++", "-std=c++17", "-O1", "-Wall", "-DB3D_SHIM_FEATURE_STAGES", f"-I{STUBS}", f"-I{SHIM}", f"-I{ROOT}/include"]
     if use_reference_headers:
         cmd += [f"-I{REF_INC}"]
     else:
