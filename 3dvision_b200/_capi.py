@@ -31,8 +31,15 @@ SYMBOLS = [
     "b3d_correspondences_devptr", "b3d_set_score_mode", "b3d_ransac_prepare", "b3d_ransac_score", "b3d_ransac_reduce", "b3d_ransac_finish",
     "b3d_ransac_counts", "b3d_ransac_hypotheses", "b3d_set_icp_mode", "b3d_icp_run", "b3d_icp_nearest",
     "b3d_kernel_launches", "b3d_stage_ms", "b3d_measure_fp32_rate", "b3d_score_recounts",
-    "b3d_voxel_downsample", "b3d_set_voxel_order_mode", "b3d_estimate_normals", "b3d_compute_fpfh",
+    "b3d_prepare_model", "b3d_register_scene", "b3d_voxel_downsample", "b3d_set_voxel_order_mode", "b3d_estimate_normals", "b3d_compute_fpfh",
 ]
+
+
+class SceneResult(C.Structure):
+    """b3d_scene_result (include/b3d.h)."""
+    _fields_ = [("coarse_T", C.c_float * 16), ("coarse_fitness", C.c_float), ("coarse_rmse", C.c_float),
+                ("coarse_best_iteration", C.c_int32), ("T", C.c_float * 16), ("fitness", C.c_float), ("rmse", C.c_float),
+                ("icp_iterations", C.c_int32), ("n_source_points", C.c_uint32)]
 
 
 class B3DError(RuntimeError):
@@ -102,6 +109,9 @@ def _declare(L):
     L.b3d_score_recounts.argtypes = [_vp, C.POINTER(C.c_uint64)]
     L.b3d_voxel_downsample.argtypes = [_vp, _vp, C.c_size_t, _vp, C.c_float, _vp, _vp, C.c_size_t, C.POINTER(C.c_size_t)]
     L.b3d_set_voxel_order_mode.argtypes = [_vp, C.c_int]
+    L.b3d_prepare_model.argtypes = [_vp, _vp, C.c_size_t, C.c_float, C.c_int, C.c_float, C.POINTER(C.c_size_t)]
+    L.b3d_register_scene.argtypes = [_vp, _vp, C.c_size_t, C.c_float, C.c_int, C.c_float, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int,
+                                     C.POINTER(SceneResult)]
     L.b3d_estimate_normals.argtypes = [_vp, _vp, C.c_size_t, C.c_int, _vp]
     L.b3d_compute_fpfh.argtypes = [_vp, _vp, _vp, C.c_size_t, C.c_float, _vp]
 
@@ -310,6 +320,29 @@ class Context:
                                         int(bool(point_to_plane)), int(bool(stop_on_convergence)),
                                         T.ctypes.data_as(_f32p), C.byref(fit), C.byref(rm), C.byref(it)))
         return _T_from_colmajor(T), fit.value, rm.value, it.value
+
+    # ---- whole registration, resident (pipeline.cpp:86-129 as one call)
+    def prepare_model(self, model_xyz, voxel_size, normals_k=30, fpfh_radius=None) -> int:
+        xyz = _as_f32(model_xyz, 3)
+        m = C.c_size_t()
+        radius = voxel_size * 5.0 if fpfh_radius is None else fpfh_radius       # pipeline.cpp:95
+        self._check(self._L.b3d_prepare_model(self._h, _ptr(xyz), xyz.shape[0], voxel_size, int(normals_k), radius, C.byref(m)))
+        self._n_tgt = m.value
+        return m.value
+
+    def register_scene(self, scene_xyz, voxel_size, normals_k=30, fpfh_radius=None, ransac_max_iterations=100000, confidence=0.999,
+                       icp_threshold=None, icp_max_iterations=200, point_to_plane=True):
+        """-> dict(coarse=(T, fitness, rmse, best_iteration), refined=(T, fitness, rmse, iterations), n_source_points)."""
+        xyz = _as_f32(scene_xyz, 3)
+        radius = voxel_size * 5.0 if fpfh_radius is None else fpfh_radius
+        thr = voxel_size * 0.4 if icp_threshold is None else icp_threshold      # pipeline_config.hpp:28
+        r = SceneResult()
+        self._check(self._L.b3d_register_scene(self._h, _ptr(xyz), xyz.shape[0], voxel_size, int(normals_k), radius, int(ransac_max_iterations),
+                                               confidence, thr, int(icp_max_iterations), int(bool(point_to_plane)), C.byref(r)))
+        self._n_src = r.n_source_points; self._H = int(ransac_max_iterations)
+        return {"coarse": (_T_from_colmajor(np.array(r.coarse_T, np.float32)), r.coarse_fitness, r.coarse_rmse, r.coarse_best_iteration),
+                "refined": (_T_from_colmajor(np.array(r.T, np.float32)), r.fitness, r.rmse, r.icp_iterations),
+                "n_source_points": int(r.n_source_points)}
 
     # ---- stages feeding the hot path (registration.cpp:29-60, 105-130, 133-201)
     def voxel_downsample(self, xyz, voxel_size, colors=None):

@@ -167,7 +167,7 @@ int b3d_set_clouds(b3d_ctx* c, const float* src_xyz, size_t n_src, const float* 
     if ((n_src && !src_xyz) || (n_tgt && !tgt_xyz)) return fail(c, B3D_ERR_INVALID, "set_clouds: null cloud pointer");
     if (n_src >= 0xFFFFFFFFull || n_tgt >= 0xFFFFFFFFull) return fail(c, B3D_ERR_INVALID, "set_clouds: more than 2^32-2 points");
     B3D_CUDA(c, cudaSetDevice(c->device));
-    c->have_clouds = false; c->have_corr = false; c->prepared = false; c->scored = false;
+    c->have_clouds = false; c->have_corr = false; c->prepared = false; c->scored = false; c->model_ready = false;
     int rc = upload_cloud(c, src_xyz, n_src, on_device, c->stage_a, c->src4); if (rc) return rc;
     rc = upload_cloud(c, tgt_xyz, n_tgt, on_device, c->stage_b, c->tgt4); if (rc) return rc;
     c->has_normals = tgt_normals != nullptr;
@@ -216,6 +216,21 @@ int b3d_voxel_downsample(b3d_ctx* c, const float* xyz, size_t n, const float* co
     if (!c || !out_n || (n && (!xyz || !out_xyz))) return B3D_ERR_INVALID;
     B3D_CUDA(c, cudaSetDevice(c->device));
     return voxel_downsample_impl(c, xyz, n, colors_or_null, voxel_size, out_xyz, out_colors_or_null, capacity, out_n);
+}
+
+int b3d_prepare_model(b3d_ctx* c, const float* model_xyz, size_t n, float voxel_size, int normals_k, float fpfh_radius, size_t* out_n_points) {
+    if (!c || (n && !model_xyz)) return B3D_ERR_INVALID;
+    B3D_CUDA(c, cudaSetDevice(c->device));
+    return prepare_model_impl(c, model_xyz, n, voxel_size, normals_k, fpfh_radius, out_n_points);
+}
+
+int b3d_register_scene(b3d_ctx* c, const float* scene_xyz, size_t n, float voxel_size, int normals_k, float fpfh_radius,
+                       int ransac_max_iterations, float ransac_confidence, float icp_distance_threshold, int icp_max_iterations,
+                       int point_to_plane, b3d_scene_result* out) {
+    if (!c || !out || (n && !scene_xyz)) return B3D_ERR_INVALID;
+    B3D_CUDA(c, cudaSetDevice(c->device));
+    return register_scene_impl(c, scene_xyz, n, voxel_size, normals_k, fpfh_radius, ransac_max_iterations, ransac_confidence,
+                               icp_distance_threshold, icp_max_iterations, point_to_plane, out);
 }
 
 int b3d_set_voxel_order_mode(b3d_ctx* c, int mode) {

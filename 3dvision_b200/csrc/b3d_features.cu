@@ -33,7 +33,7 @@ namespace b3d {
 
 // fbuf slots
 enum { F_PTS4 = 0, F_NRM4, F_SLOTS, F_GP, F_SORTED, F_PT_SLOT, F_PT_RANK, F_COV, F_OUT, F_NBR, F_NBR_CNT, F_SPFH,
-       F_KEYS_A, F_KEYS_B, F_IDX_A, F_IDX_B, F_CUB, F_SEG, F_VOX_MEAN, F_VOX_COL, F_VOX_KEY, F_VOX_FIRST, F_VOX_ORDER, F_PERM, F_RAW, F_RAW2, F_ORD_OPEN, F_ORD_KEYS, F_ORD_SEQ };
+       F_KEYS_A, F_KEYS_B, F_IDX_A, F_IDX_B, F_CUB, F_SEG, F_VOX_MEAN, F_VOX_COL, F_VOX_KEY, F_VOX_FIRST, F_VOX_ORDER, F_PERM, F_RAW, F_RAW2, F_ORD_OPEN, F_ORD_KEYS, F_ORD_SEQ, F_PIPE_NRM };
 
 constexpr int kFeatWarps = 8;                 // warps (= queries in flight) per block
 constexpr int kKeyBuf = 256;                  // per-warp key buffer: sorted prefix + staged candidates
@@ -558,15 +558,11 @@ static int upload_points(b3d_ctx* c, const float* xyz, size_t n, int raw_slot, i
     return xyz_to_float4(c, c->fbuf[raw_slot].as<float>(), n, c->fbuf[dst_slot].as<float4>());
 }
 
-int estimate_normals_impl(b3d_ctx* c, const float* xyz, size_t n_, int k, float* out_normals) {
-    if (n_ == 0) return B3D_OK;
+// device core: pts (float4, n) -> d_out (packed xyz normals, n)
+int estimate_normals_dev(b3d_ctx* c, const float4* pts, unsigned n, int k, float* d_out) {
     if (k < 1 || k > kMaxList) return fail(c, B3D_ERR_INVALID, "estimate_normals: k must be in [1, 128]");
-    if (n_ > 0x7FFFFFFFu) return fail(c, B3D_ERR_INVALID, "estimate_normals: too many points");
     StageTimer timer(c, 8);
-    const unsigned n = (unsigned)n_;
-    int rc = upload_points(c, xyz, n, F_RAW, F_PTS4);
-    if (rc != B3D_OK) return rc;
-    const float4* pts = c->fbuf[F_PTS4].as<float4>();
+    int rc;
     const unsigned K = (unsigned)k < n ? (unsigned)k : n;
     // Cell edge: aim at ~16 points per occupied cell, for which one 3x3x3 block almost always settles a 30-NN query.
     // Density is only known after a build, so start from a bounding-cube guess and correct it (surface scaling,
@@ -591,13 +587,46 @@ int estimate_normals_impl(b3d_ctx* c, const float* xyz, size_t n_, int k, float*
         cell = next;
     }
     B3D_CUDA(c, c->fbuf[F_COV].ensure(sizeof(float) * 9 * n));
-    B3D_CUDA(c, c->fbuf[F_OUT].ensure(sizeof(float) * 3 * n));
     knn_covariance_kernel<<<grid_for(n, kFeatWarps, 16), kFeatWarps * 32, 0, c->stream>>>(pts, n, K, g.slots, g.sorted, g.gp, c->fbuf[F_COV].as<float>());
     B3D_LAUNCHED(c);
-    normal_from_covariance_kernel<<<div_up(n, 128), 128, 0, c->stream>>>(pts, c->fbuf[F_COV].as<float>(), n, c->fbuf[F_OUT].as<float>());
+    normal_from_covariance_kernel<<<div_up(n, 128), 128, 0, c->stream>>>(pts, c->fbuf[F_COV].as<float>(), n, d_out);
     B3D_LAUNCHED(c);
+    return B3D_OK;
+}
+
+int estimate_normals_impl(b3d_ctx* c, const float* xyz, size_t n_, int k, float* out_normals) {
+    if (n_ == 0) return B3D_OK;
+    if (n_ > 0x7FFFFFFFu) return fail(c, B3D_ERR_INVALID, "estimate_normals: too many points");
+    const unsigned n = (unsigned)n_;
+    int rc = upload_points(c, xyz, n, F_RAW, F_PTS4);
+    if (rc != B3D_OK) return rc;
+    B3D_CUDA(c, c->fbuf[F_OUT].ensure(sizeof(float) * 3 * n));
+    rc = estimate_normals_dev(c, c->fbuf[F_PTS4].as<float4>(), n, k, c->fbuf[F_OUT].as<float>());
+    if (rc != B3D_OK) return rc;
     B3D_CUDA(c, cudaMemcpyAsync(out_normals, c->fbuf[F_OUT].p, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, c->stream));
     B3D_CUDA(c, cudaStreamSynchronize(c->stream));
+    return B3D_OK;
+}
+
+// device core: pts / nrm (float4, n) -> d_out (n x 33)
+int compute_fpfh_dev(b3d_ctx* c, const float4* pts, const float4* nrm, unsigned n, float radius, float* d_out) {
+    if (n > 0x7FFFFFFFu / kFpfhMaxNn) return fail(c, B3D_ERR_INVALID, "compute_fpfh: too many points");
+    StageTimer timer(c, 9);
+    const float r2 = radius * radius;                                               // registration.cpp:90
+    PointGrid g;
+    int rc = build_point_grid(c, pts, n, radius * 1.02f, &g);
+    if (rc != B3D_OK) return rc;
+    B3D_CUDA(c, c->fbuf[F_NBR].ensure(sizeof(unsigned) * kFpfhMaxNn * (size_t)n));
+    B3D_CUDA(c, c->fbuf[F_NBR_CNT].ensure(sizeof(unsigned) * n));
+    B3D_CUDA(c, c->fbuf[F_SPFH].ensure(sizeof(float) * 33 * (size_t)n));
+    unsigned* nbr = c->fbuf[F_NBR].as<unsigned>(); unsigned* cnt = c->fbuf[F_NBR_CNT].as<unsigned>();
+    const int blocks = grid_for(n, kFeatWarps, 16);
+    radius_neighbors_kernel<<<blocks, kFeatWarps * 32, 0, c->stream>>>(pts, n, r2, g.slots, g.sorted, g.gp, nbr, cnt);
+    B3D_LAUNCHED(c);
+    spfh_kernel<<<blocks, kFeatWarps * 32, 0, c->stream>>>(pts, nrm, n, nbr, cnt, c->fbuf[F_SPFH].as<float>());
+    B3D_LAUNCHED(c);
+    fpfh_kernel<<<blocks, kFeatWarps * 32, 0, c->stream>>>(pts, n, nbr, cnt, c->fbuf[F_SPFH].as<float>(), d_out);
+    B3D_LAUNCHED(c);
     return B3D_OK;
 }
 
@@ -605,53 +634,25 @@ int compute_fpfh_impl(b3d_ctx* c, const float* xyz, const float* normals, size_t
     if (n_ == 0) return B3D_OK;
     if (!normals) return fail(c, B3D_ERR_INVALID, "compute_fpfh: normals required");
     if (n_ > 0x7FFFFFFFu / kFpfhMaxNn) return fail(c, B3D_ERR_INVALID, "compute_fpfh: too many points");
-    StageTimer timer(c, 9);
     const unsigned n = (unsigned)n_;
     int rc = upload_points(c, xyz, n, F_RAW, F_PTS4);
     if (rc != B3D_OK) return rc;
     rc = upload_points(c, normals, n, F_RAW2, F_NRM4);
     if (rc != B3D_OK) return rc;
-    const float4* pts = c->fbuf[F_PTS4].as<float4>();
-    const float r2 = radius * radius;                                               // registration.cpp:90
-    PointGrid g;
-    rc = build_point_grid(c, pts, n, radius * 1.02f, &g);
-    if (rc != B3D_OK) return rc;
-    B3D_CUDA(c, c->fbuf[F_NBR].ensure(sizeof(unsigned) * kFpfhMaxNn * (size_t)n));
-    B3D_CUDA(c, c->fbuf[F_NBR_CNT].ensure(sizeof(unsigned) * n));
-    B3D_CUDA(c, c->fbuf[F_SPFH].ensure(sizeof(float) * 33 * (size_t)n));
     B3D_CUDA(c, c->fbuf[F_OUT].ensure(sizeof(float) * 33 * (size_t)n));
-    unsigned* nbr = c->fbuf[F_NBR].as<unsigned>(); unsigned* cnt = c->fbuf[F_NBR_CNT].as<unsigned>();
-    const int blocks = grid_for(n, kFeatWarps, 16);
-    radius_neighbors_kernel<<<blocks, kFeatWarps * 32, 0, c->stream>>>(pts, n, r2, g.slots, g.sorted, g.gp, nbr, cnt);
-    B3D_LAUNCHED(c);
-    spfh_kernel<<<blocks, kFeatWarps * 32, 0, c->stream>>>(pts, c->fbuf[F_NRM4].as<float4>(), n, nbr, cnt, c->fbuf[F_SPFH].as<float>());
-    B3D_LAUNCHED(c);
-    fpfh_kernel<<<blocks, kFeatWarps * 32, 0, c->stream>>>(pts, n, nbr, cnt, c->fbuf[F_SPFH].as<float>(), c->fbuf[F_OUT].as<float>());
-    B3D_LAUNCHED(c);
+    rc = compute_fpfh_dev(c, c->fbuf[F_PTS4].as<float4>(), c->fbuf[F_NRM4].as<float4>(), n, radius, c->fbuf[F_OUT].as<float>());
+    if (rc != B3D_OK) return rc;
     B3D_CUDA(c, cudaMemcpyAsync(out_desc, c->fbuf[F_OUT].p, sizeof(float) * 33 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
     B3D_CUDA(c, cudaStreamSynchronize(c->stream));
     return B3D_OK;
 }
 
-int voxel_downsample_impl(b3d_ctx* c, const float* xyz, size_t n_, const float* colors, float voxel, float* out_xyz, float* out_colors,
-                          size_t capacity, size_t* out_n) {
-    *out_n = 0;
-    if (n_ == 0) return B3D_OK;
+// device core: d_xyz / d_col (packed, n) -> packed means in fbuf[F_OUT] (*d_out_xyz, *d_out_col), *m_out voxels, reference order
+int voxel_downsample_dev(b3d_ctx* c, const float* d_xyz, unsigned n, const float* d_col, float voxel, float** d_out_xyz, float** d_out_col_p,
+                         unsigned* m_out) {
     if (!(voxel > 0.0f)) return fail(c, B3D_ERR_INVALID, "voxel_downsample: voxel_size must be positive");
-    if (n_ > 0x7FFFFFFFu) return fail(c, B3D_ERR_INVALID, "voxel_downsample: too many points");
-    if (colors && !out_colors) return fail(c, B3D_ERR_INVALID, "voxel_downsample: colors given but no output for them");
     StageTimer timer(c, 7);
-    const unsigned n = (unsigned)n_;
     const float inv = 1.0f / voxel;                                                 // registration.cpp:32
-    B3D_CUDA(c, c->fbuf[F_RAW].ensure(sizeof(float) * 3 * n));
-    B3D_CUDA(c, cudaMemcpyAsync(c->fbuf[F_RAW].p, xyz, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, c->stream));
-    const float* d_xyz = c->fbuf[F_RAW].as<float>();
-    const float* d_col = nullptr;
-    if (colors) {
-        B3D_CUDA(c, c->fbuf[F_RAW2].ensure(sizeof(float) * 3 * n));
-        B3D_CUDA(c, cudaMemcpyAsync(c->fbuf[F_RAW2].p, colors, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, c->stream));
-        d_col = c->fbuf[F_RAW2].as<float>();
-    }
     B3D_CUDA(c, c->fbuf[F_KEYS_A].ensure(sizeof(unsigned long long) * n)); B3D_CUDA(c, c->fbuf[F_KEYS_B].ensure(sizeof(unsigned long long) * n));
     B3D_CUDA(c, c->fbuf[F_IDX_A].ensure(sizeof(unsigned) * n));            B3D_CUDA(c, c->fbuf[F_IDX_B].ensure(sizeof(unsigned) * n));
     B3D_CUDA(c, c->fbuf[F_SEG].ensure(sizeof(unsigned) * (n + 4)));
@@ -681,16 +682,15 @@ int voxel_downsample_impl(b3d_ctx* c, const float* xyz, size_t n_, const float* 
     B3D_CUDA(c, cudaStreamSynchronize(c->stream));
     if (h_flags[0]) return fail(c, B3D_ERR_INVALID, "voxel_downsample: |coordinate / voxel_size| must stay below 2^20");
     const unsigned m = h_flags[1];
-    *out_n = m;
-    if (m > capacity) return fail(c, B3D_ERR_INVALID, "voxel_downsample: output capacity too small (out_n holds the size needed)");
+    *m_out = m;
     B3D_CUDA(c, c->fbuf[F_VOX_MEAN].ensure(sizeof(float) * 3 * m));
-    if (colors) B3D_CUDA(c, c->fbuf[F_VOX_COL].ensure(sizeof(float) * 3 * m));
+    if (d_col) B3D_CUDA(c, c->fbuf[F_VOX_COL].ensure(sizeof(float) * 3 * m));
     B3D_CUDA(c, c->fbuf[F_VOX_KEY].ensure(sizeof(int) * 3 * m * 2));                // [0, 3m) by voxel, [3m, 6m) in first-appearance order
     B3D_CUDA(c, c->fbuf[F_VOX_FIRST].ensure(sizeof(unsigned) * m * 2));
     B3D_CUDA(c, c->fbuf[F_VOX_ORDER].ensure(sizeof(unsigned) * m * 2));
     B3D_CUDA(c, c->fbuf[F_PERM].ensure(sizeof(unsigned) * m));
     B3D_CUDA(c, c->fbuf[F_OUT].ensure(sizeof(float) * 3 * m * 2));
-    float* mean = c->fbuf[F_VOX_MEAN].as<float>(); float* mean_col = colors ? c->fbuf[F_VOX_COL].as<float>() : nullptr;
+    float* mean = c->fbuf[F_VOX_MEAN].as<float>(); float* mean_col = d_col ? c->fbuf[F_VOX_COL].as<float>() : nullptr;
     int* key3 = c->fbuf[F_VOX_KEY].as<int>(); int* key3_ordered = key3 + 3 * (size_t)m;
     unsigned* first = c->fbuf[F_VOX_FIRST].as<unsigned>(); unsigned* first_sorted = first + m;
     unsigned* vox = c->fbuf[F_VOX_ORDER].as<unsigned>(); unsigned* order = vox + m;
@@ -719,13 +719,97 @@ int voxel_downsample_impl(b3d_ctx* c, const float* xyz, size_t n_, const float* 
         int rc = container_order_device(c, key3_ordered, m, c->fbuf[F_PERM].as<unsigned>());
         if (rc != B3D_OK) return rc;
     }
-    float* d_out = c->fbuf[F_OUT].as<float>(); float* d_out_col = colors ? d_out + 3 * (size_t)m : nullptr;
+    float* d_out = c->fbuf[F_OUT].as<float>(); float* d_out_col = d_col ? d_out + 3 * (size_t)m : nullptr;
     gather_voxels_kernel<<<div_up(m, 256), 256, 0, c->stream>>>(mean, mean_col, order, c->fbuf[F_PERM].as<unsigned>(), m, d_out, d_out_col);
     B3D_LAUNCHED(c);
+    *d_out_xyz = d_out; *d_out_col_p = d_out_col;
+    return B3D_OK;
+}
+
+int voxel_downsample_impl(b3d_ctx* c, const float* xyz, size_t n_, const float* colors, float voxel, float* out_xyz, float* out_colors,
+                          size_t capacity, size_t* out_n) {
+    *out_n = 0;
+    if (n_ == 0) return B3D_OK;
+    if (n_ > 0x7FFFFFFFu) return fail(c, B3D_ERR_INVALID, "voxel_downsample: too many points");
+    if (colors && !out_colors) return fail(c, B3D_ERR_INVALID, "voxel_downsample: colors given but no output for them");
+    const unsigned n = (unsigned)n_;
+    B3D_CUDA(c, c->fbuf[F_RAW].ensure(sizeof(float) * 3 * n));
+    B3D_CUDA(c, cudaMemcpyAsync(c->fbuf[F_RAW].p, xyz, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, c->stream));
+    const float* d_col = nullptr;
+    if (colors) {
+        B3D_CUDA(c, c->fbuf[F_RAW2].ensure(sizeof(float) * 3 * n));
+        B3D_CUDA(c, cudaMemcpyAsync(c->fbuf[F_RAW2].p, colors, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, c->stream));
+        d_col = c->fbuf[F_RAW2].as<float>();
+    }
+    float* d_out = nullptr; float* d_out_col = nullptr; unsigned m = 0;
+    int rc = voxel_downsample_dev(c, c->fbuf[F_RAW].as<float>(), n, d_col, voxel, &d_out, &d_out_col, &m);
+    if (rc != B3D_OK) return rc;
+    *out_n = m;
+    if (m > capacity) return fail(c, B3D_ERR_INVALID, "voxel_downsample: output capacity too small (out_n holds the size needed)");
     B3D_CUDA(c, cudaMemcpyAsync(out_xyz, d_out, sizeof(float) * 3 * m, cudaMemcpyDeviceToHost, c->stream));
     if (colors) B3D_CUDA(c, cudaMemcpyAsync(out_colors, d_out_col, sizeof(float) * 3 * m, cudaMemcpyDeviceToHost, c->stream));
     B3D_CUDA(c, cudaStreamSynchronize(c->stream));
     return B3D_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// One call per side of a registration, everything resident: raw points in, (points, normals, FPFH) left on the device
+// where the matching / RANSAC / ICP stages read them.  This is the per-instance body of Pipeline::processInstance
+// (src/pipeline.cpp:86-129) without the host containers between the stages.
+// ---------------------------------------------------------------------------------
+static int prepare_cloud_resident(b3d_ctx* c, const float* xyz_host, unsigned n, float voxel, int k, float radius,
+                                  DevBuf& pts4, DevBuf& nrm4, DevBuf& desc, unsigned* m_out) {
+    B3D_CUDA(c, c->fbuf[F_RAW].ensure(sizeof(float) * 3 * (size_t)n));
+    B3D_CUDA(c, cudaMemcpyAsync(c->fbuf[F_RAW].p, xyz_host, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    float* d_down = nullptr; float* d_unused = nullptr; unsigned m = 0;
+    int rc = voxel_downsample_dev(c, c->fbuf[F_RAW].as<float>(), n, nullptr, voxel, &d_down, &d_unused, &m);
+    if (rc != B3D_OK) return rc;
+    *m_out = m;
+    if (m == 0) return B3D_OK;
+    B3D_CUDA(c, pts4.ensure(sizeof(float4) * m)); B3D_CUDA(c, nrm4.ensure(sizeof(float4) * m));
+    B3D_CUDA(c, desc.ensure(sizeof(float) * 33 * (size_t)m));
+    B3D_CUDA(c, c->fbuf[F_PIPE_NRM].ensure(sizeof(float) * 3 * (size_t)m));
+    rc = xyz_to_float4(c, d_down, m, pts4.as<float4>());
+    if (rc != B3D_OK) return rc;
+    rc = estimate_normals_dev(c, pts4.as<float4>(), m, k, c->fbuf[F_PIPE_NRM].as<float>());
+    if (rc != B3D_OK) return rc;
+    rc = xyz_to_float4(c, c->fbuf[F_PIPE_NRM].as<float>(), m, nrm4.as<float4>());
+    if (rc != B3D_OK) return rc;
+    return compute_fpfh_dev(c, pts4.as<float4>(), nrm4.as<float4>(), m, radius, desc.as<float>());
+}
+
+int prepare_model_impl(b3d_ctx* c, const float* xyz, size_t n, float voxel, int k, float radius, size_t* out_n) {
+    if (n > 0x7FFFFFFFu) return fail(c, B3D_ERR_INVALID, "prepare_model: too many points");
+    c->model_ready = false; c->have_clouds = false; c->have_feats = false; c->have_corr = false; c->prepared = false; c->scored = false;
+    unsigned m = 0;
+    if (n) { int rc = prepare_cloud_resident(c, xyz, (unsigned)n, voxel, k, radius, c->tgt4, c->nrm4, c->tdesc, &m); if (rc != B3D_OK) return rc; }
+    B3D_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->n_tgt = m; c->has_normals = m > 0; c->tdesc_p = c->tdesc.as<float>();
+    c->model_ready = true;
+    if (out_n) *out_n = m;
+    return B3D_OK;
+}
+
+int register_scene_impl(b3d_ctx* c, const float* xyz, size_t n, float voxel, int k, float radius, int ransac_iterations, float confidence,
+                        float icp_threshold, int icp_iterations, int point_to_plane, b3d_scene_result* out) {
+    if (!c->model_ready) return fail(c, B3D_ERR_STATE, "register_scene: call b3d_prepare_model first");
+    if (n > 0x7FFFFFFFu) return fail(c, B3D_ERR_INVALID, "register_scene: too many points");
+    for (int i = 0; i < 16; ++i) out->coarse_T[i] = out->T[i] = (i % 5 == 0) ? 1.0f : 0.0f;    // RegistrationResult defaults (registration.hpp:27-29)
+    out->coarse_fitness = out->coarse_rmse = out->fitness = out->rmse = 0.0f;
+    out->coarse_best_iteration = -1; out->icp_iterations = 0; out->n_source_points = 0;
+    c->have_clouds = false; c->have_feats = false; c->have_corr = false; c->prepared = false; c->scored = false;
+    unsigned m = 0;
+    if (n) { int rc = prepare_cloud_resident(c, xyz, (unsigned)n, voxel, k, radius, c->src4, c->fbuf[F_NRM4], c->sdesc, &m); if (rc != B3D_OK) return rc; }
+    out->n_source_points = m;
+    c->n_src = m; c->sdesc_p = c->sdesc.as<float>();
+    c->have_clouds = true; c->have_feats = true;
+    int rc = b3d_match_features(c, 0, m); if (rc != B3D_OK) return rc;
+    rc = b3d_ransac_prepare(c, voxel, ransac_iterations, confidence); if (rc != B3D_OK) return rc;
+    rc = b3d_ransac_score(c, 0, ransac_iterations); if (rc != B3D_OK) return rc;
+    int64_t* keys = reinterpret_cast<int64_t*>(&c->state.as<DeviceState>()->best_key);
+    rc = b3d_ransac_reduce(c, 0, ransac_iterations, nullptr, keys); if (rc != B3D_OK) return rc;
+    rc = b3d_ransac_finish(c, keys, out->coarse_T, &out->coarse_fitness, &out->coarse_rmse, &out->coarse_best_iteration); if (rc != B3D_OK) return rc;
+    return b3d_icp_run(c, out->coarse_T, icp_threshold, icp_iterations, point_to_plane, 1, out->T, &out->fitness, &out->rmse, &out->icp_iterations);
 }
 
 }  // namespace b3d

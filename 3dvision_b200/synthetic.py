@@ -58,6 +58,27 @@ def torus(n, rng, R=0.08, r=0.03, center=(0.0, 0.0, 0.6)):
     return (P + np.asarray(center)).astype(np.float32), nrm.astype(np.float32)
 
 
+_ROUGH = np.random.default_rng(977)
+_ROUGH_F = _ROUGH.integers(1, 14, 32); _ROUGH_G = _ROUGH.integers(0, 7, 32)
+_ROUGH_A = _ROUGH.uniform(0.3, 1.0, 32) / np.sqrt(32.0); _ROUGH_P = _ROUGH.uniform(0, 2 * np.pi, 32)
+
+
+def rough_torus(n, rng, R=0.25, r=0.09, rough=0.18, center=(0.0, 0.0, 0.6)):
+    """The bumpy torus with a fixed random Fourier relief on the tube radius (features of a few centimetres, amplitude
+    ~rough*r): locally distinctive geometry, so real FPFH descriptors can tell places apart. Points only."""
+    u = rng.uniform(0, 2 * np.pi, n)
+    v = rng.uniform(0, 2 * np.pi, n)
+    relief = np.zeros(n)
+    for f, g, a, p in zip(_ROUGH_F, _ROUGH_G, _ROUGH_A, _ROUGH_P):
+        relief += a * np.cos(f * u + g * v + p)
+    rho = R * (1.0 + 0.20 * np.cos(2.0 * u) + 0.10 * np.sin(3.0 * u))
+    rr = r * (1.0 + 0.30 * np.cos(u + 1.0)) * (1.0 + rough * relief)
+    x = (rho + rr * np.cos(v)) * np.cos(u)
+    y = (rho + rr * np.cos(v)) * np.sin(u)
+    z = rr * np.sin(v) + 0.25 * R * np.sin(2.0 * u + 0.3)
+    return (np.stack([x, y, z], 1) + np.asarray(center)).astype(np.float32)
+
+
 def histograms(n, rng, sparsity=0.5):
     """n x 33 non-negative, L1-normalised descriptors shaped like FPFH rows (registration.cpp:192-194)."""
     d = rng.gamma(0.6, 1.0, (n, 33))

@@ -168,6 +168,27 @@ int b3d_estimate_normals(b3d_ctx* ctx, const float* xyz, size_t n, int k, float*
  * order; L1 normalisation.  out_desc is n x 33. */
 int b3d_compute_fpfh(b3d_ctx* ctx, const float* xyz, const float* normals, size_t n, float radius, float* out_desc);
 
+/* ---- one call per registration, everything resident ------------------------------------------------
+ * The per-instance body of Pipeline::processInstance (src/pipeline.cpp:86-129: voxelDownsample ->
+ * estimateNormals -> computeFPFH -> ransacRegistration -> icpRefine) as ONE call, with the model side
+ * prepared once per run as Pipeline::run does with the reference model (src/pipeline.cpp:275-294).
+ * Identical results to the five separate calls (tests/test_gpu_features.py); no host containers and no
+ * PCIe round trips between the stages.  b3d_set_clouds / b3d_ransac / b3d_icp replace the resident model. */
+typedef struct b3d_scene_result {
+    float coarse_T[16];             /* ransacRegistration result, column-major */
+    float coarse_fitness, coarse_rmse;
+    int32_t coarse_best_iteration;  /* -1 if no hypothesis had an inlier */
+    float T[16];                    /* icpRefine result */
+    float fitness, rmse;
+    int32_t icp_iterations;
+    uint32_t n_source_points;       /* scene points after down-sampling */
+} b3d_scene_result;
+int b3d_prepare_model(b3d_ctx* ctx, const float* model_xyz, size_t n, float voxel_size, int normals_k, float fpfh_radius,
+                      size_t* out_n_points);
+int b3d_register_scene(b3d_ctx* ctx, const float* scene_xyz, size_t n, float voxel_size, int normals_k, float fpfh_radius,
+                       int ransac_max_iterations, float ransac_confidence, float icp_distance_threshold, int icp_max_iterations,
+                       int point_to_plane, b3d_scene_result* out);
+
 /* Point-to-point accumulation: 0 (default) = add the matched pairs in source order in fp32, exactly
  * as src/registration.cpp:341, 374-386 does (bit-identical sums; one sequential dependency chain per
  * sum, so large clouds cost ~5 cycles per matched point per pass); 1 = deterministic fp64 tree sums

@@ -166,3 +166,40 @@ def test_demo_scene_front_end_matches_golden_digests(ctx, oracle):
     coarse = R.ransacRegistration(src, tgt, src_f, tgt_f, voxel, g["ransac_max_iterations"], g["confidence"])
     assert np.array_equal(coarse.transformation.reshape(-1), np.asarray(g["ransac"]["T"], np.float32))
     assert np.float32(coarse.fitness) == np.float32(g["ransac"]["fitness"]) and np.float32(coarse.rmse) == np.float32(g["ransac"]["rmse"])
+
+
+# ------------------------------------------------------------------ the whole per-instance body as one resident call
+def test_register_scene_equals_the_five_separate_calls(b3d, ctx):
+    rng = np.random.default_rng(77)
+    voxel = 0.006
+    model_raw = syn.rough_torus(60000, rng)
+    T_true = syn.rigid([0.2, 0.9, -0.3], 25.0, [0.05, -0.03, 0.08])
+    scene_raw = (syn.apply(np.linalg.inv(T_true), syn.rough_torus(60000, rng)) + rng.normal(0, 0.0003, (60000, 3))).astype(np.float32)
+    R = reg.Registration
+    tgt = R.voxelDownsample(reg.PointCloud(model_raw), voxel); R.estimateNormals(tgt, 30); tgt_f = R.computeFPFH(tgt, voxel * 5.0)
+    src = R.voxelDownsample(reg.PointCloud(scene_raw), voxel); R.estimateNormals(src, 30); src_f = R.computeFPFH(src, voxel * 5.0)
+    coarse = R.ransacRegistration(src, tgt, src_f, tgt_f, voxel, 20000, 0.999)
+    fine = R.icpRefine(src, tgt, coarse.transformation, voxel * 0.4, 50, True)
+    c2 = b3d.Context(0)
+    try:
+        assert c2.prepare_model(model_raw, voxel) == tgt.size()
+        for _ in range(2):                                      # the model stays resident across scenes
+            out = c2.register_scene(scene_raw, voxel, ransac_max_iterations=20000, icp_max_iterations=50)
+            assert out["n_source_points"] == src.size()
+            T0, f0, r0, _ = out["coarse"]; T1, f1, r1, _ = out["refined"]
+            assert np.array_equal(T0, coarse.transformation) and f0 == coarse.fitness and r0 == coarse.rmse
+            assert np.array_equal(T1, fine.transformation) and f1 == fine.fitness and r1 == fine.rmse
+        assert syn.rotation_error(T1, T_true) < 2e-3 and syn.translation_error(T1, T_true) < 1e-3      # and it registered
+        empty = c2.register_scene(np.zeros((0, 3), np.float32), voxel)
+        assert np.array_equal(empty["refined"][0], np.eye(4, dtype=np.float32)) and empty["refined"][1] == 0.0
+    finally:
+        c2.close()
+
+
+def test_register_scene_requires_a_model(b3d):
+    c2 = b3d.Context(0)
+    try:
+        with pytest.raises(b3d.B3DError):
+            c2.register_scene(np.zeros((10, 3), np.float32), 0.01)
+    finally:
+        c2.close()
