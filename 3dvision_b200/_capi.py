@@ -31,7 +31,7 @@ SYMBOLS = [
     "b3d_correspondences_devptr", "b3d_set_score_mode", "b3d_ransac_prepare", "b3d_ransac_score", "b3d_ransac_reduce", "b3d_ransac_finish",
     "b3d_ransac_counts", "b3d_ransac_hypotheses", "b3d_set_icp_mode", "b3d_icp_run", "b3d_icp_nearest",
     "b3d_kernel_launches", "b3d_stage_ms", "b3d_measure_fp32_rate", "b3d_score_recounts",
-    "b3d_prepare_model", "b3d_register_scene", "b3d_voxel_downsample", "b3d_set_voxel_order_mode", "b3d_estimate_normals", "b3d_compute_fpfh",
+    "b3d_prepare_model", "b3d_register_scene", "b3d_depth_to_cloud", "b3d_register_depth", "b3d_voxel_downsample", "b3d_set_voxel_order_mode", "b3d_estimate_normals", "b3d_compute_fpfh",
 ]
 
 
@@ -109,6 +109,10 @@ def _declare(L):
     L.b3d_score_recounts.argtypes = [_vp, C.POINTER(C.c_uint64)]
     L.b3d_voxel_downsample.argtypes = [_vp, _vp, C.c_size_t, _vp, C.c_float, _vp, _vp, C.c_size_t, C.POINTER(C.c_size_t)]
     L.b3d_set_voxel_order_mode.argtypes = [_vp, C.c_int]
+    L.b3d_depth_to_cloud.argtypes = [_vp, _vp, C.c_int, C.c_int, _vp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _vp,
+                                     _vp, _vp, C.c_size_t, C.POINTER(C.c_size_t)]
+    L.b3d_register_depth.argtypes = [_vp, _vp, C.c_int, C.c_int, _vp] + [C.c_float] * 6 + [C.c_float, C.c_int, C.c_float, C.c_int, C.c_float,
+                                     C.c_float, C.c_int, C.c_int, C.POINTER(SceneResult)]
     L.b3d_prepare_model.argtypes = [_vp, _vp, C.c_size_t, C.c_float, C.c_int, C.c_float, C.POINTER(C.c_size_t)]
     L.b3d_register_scene.argtypes = [_vp, _vp, C.c_size_t, C.c_float, C.c_int, C.c_float, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int,
                                      C.POINTER(SceneResult)]
@@ -339,6 +343,32 @@ class Context:
         r = SceneResult()
         self._check(self._L.b3d_register_scene(self._h, _ptr(xyz), xyz.shape[0], voxel_size, int(normals_k), radius, int(ransac_max_iterations),
                                                confidence, thr, int(icp_max_iterations), int(bool(point_to_plane)), C.byref(r)))
+        self._n_src = r.n_source_points; self._H = int(ransac_max_iterations)
+        return {"coarse": (_T_from_colmajor(np.array(r.coarse_T, np.float32)), r.coarse_fitness, r.coarse_rmse, r.coarse_best_iteration),
+                "refined": (_T_from_colmajor(np.array(r.T, np.float32)), r.fitness, r.rmse, r.icp_iterations),
+                "n_source_points": int(r.n_source_points)}
+
+    def depth_to_cloud(self, depth, mask, scale_to_meters, clipping_max, fx, fy, cx, cy, bgr=None):
+        """pipeline.cpp:38-84. depth uint16 (h,w); mask uint8 (h,w) or None; bgr uint8 (h,w,3) or None -> (xyz, rgb or None)."""
+        depth = np.ascontiguousarray(depth, np.uint16); h, w = depth.shape
+        mask = np.ascontiguousarray(mask, np.uint8) if mask is not None else None
+        bgr = np.ascontiguousarray(bgr, np.uint8) if bgr is not None else None
+        xyz = np.empty((h * w, 3), np.float32); rgb = np.empty((h * w, 3), np.float32) if bgr is not None else None
+        n = C.c_size_t()
+        self._check(self._L.b3d_depth_to_cloud(self._h, _ptr(depth), w, h, _ptr(mask), scale_to_meters, clipping_max, fx, fy, cx, cy, _ptr(bgr),
+                                               _ptr(xyz), _ptr(rgb), h * w, C.byref(n)))
+        return xyz[:n.value].copy(), (rgb[:n.value].copy() if rgb is not None else None)
+
+    def register_depth(self, depth, mask, scale_to_meters, clipping_max, fx, fy, cx, cy, voxel_size, normals_k=30, fpfh_radius=None,
+                       ransac_max_iterations=100000, confidence=0.999, icp_threshold=None, icp_max_iterations=200, point_to_plane=True):
+        depth = np.ascontiguousarray(depth, np.uint16); h, w = depth.shape
+        mask = np.ascontiguousarray(mask, np.uint8) if mask is not None else None
+        radius = voxel_size * 5.0 if fpfh_radius is None else fpfh_radius
+        thr = voxel_size * 0.4 if icp_threshold is None else icp_threshold
+        r = SceneResult()
+        self._check(self._L.b3d_register_depth(self._h, _ptr(depth), w, h, _ptr(mask), scale_to_meters, clipping_max, fx, fy, cx, cy, voxel_size,
+                                               int(normals_k), radius, int(ransac_max_iterations), confidence, thr, int(icp_max_iterations),
+                                               int(bool(point_to_plane)), C.byref(r)))
         self._n_src = r.n_source_points; self._H = int(ransac_max_iterations)
         return {"coarse": (_T_from_colmajor(np.array(r.coarse_T, np.float32)), r.coarse_fitness, r.coarse_rmse, r.coarse_best_iteration),
                 "refined": (_T_from_colmajor(np.array(r.T, np.float32)), r.fitness, r.rmse, r.icp_iterations),

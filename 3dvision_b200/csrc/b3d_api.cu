@@ -233,6 +233,26 @@ int b3d_register_scene(b3d_ctx* c, const float* scene_xyz, size_t n, float voxel
                                icp_distance_threshold, icp_max_iterations, point_to_plane, out);
 }
 
+int b3d_depth_to_cloud(b3d_ctx* c, const uint16_t* depth, int width, int height, const uint8_t* mask_or_null, float scale_to_meters,
+                       float clipping_max, float fx, float fy, float cx, float cy, const uint8_t* bgr_or_null,
+                       float* out_xyz, float* out_rgb_or_null, size_t capacity, size_t* out_n) {
+    if (!c || !depth || !out_xyz || !out_n) return B3D_ERR_INVALID;
+    B3D_CUDA(c, cudaSetDevice(c->device));
+    return depth_to_cloud_impl(c, depth, width, height, mask_or_null, scale_to_meters, clipping_max, fx, fy, cx, cy, bgr_or_null,
+                               out_xyz, out_rgb_or_null, capacity, out_n);
+}
+
+int b3d_register_depth(b3d_ctx* c, const uint16_t* depth, int width, int height, const uint8_t* mask_or_null, float scale_to_meters,
+                       float clipping_max, float fx, float fy, float cx, float cy, float voxel_size, int normals_k, float fpfh_radius,
+                       int ransac_max_iterations, float ransac_confidence, float icp_distance_threshold, int icp_max_iterations,
+                       int point_to_plane, b3d_scene_result* out) {
+    if (!c || !depth || !out) return B3D_ERR_INVALID;
+    B3D_CUDA(c, cudaSetDevice(c->device));
+    return register_depth_impl(c, depth, width, height, mask_or_null, scale_to_meters, clipping_max, fx, fy, cx, cy, voxel_size, normals_k,
+                               fpfh_radius, ransac_max_iterations, ransac_confidence, icp_distance_threshold, icp_max_iterations,
+                               point_to_plane, out);
+}
+
 int b3d_set_voxel_order_mode(b3d_ctx* c, int mode) {
     if (!c || mode < 0 || mode > 1) return B3D_ERR_INVALID;
     c->voxel_order_mode = mode;

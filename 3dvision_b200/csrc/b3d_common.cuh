@@ -101,7 +101,8 @@ struct b3d_ctx {
     b3d::DevBuf src_slots, src_sorted, src_slot, src_rank;   // source reordered by target cell (coherent warps)
 
     // feature stages (b3d_features.cu): scratch pool, slots named there
-    b3d::DevBuf fbuf[32];
+    static constexpr int kFeatureBufs = 48;
+    b3d::DevBuf fbuf[kFeatureBufs];
     bool model_ready = false;                // b3d_prepare_model has left the target cloud / normals / FPFH resident
     int voxel_order_mode = 0;                // 0: container order simulated on the device; 1: real std::unordered_map on the host
 
@@ -160,6 +161,11 @@ int voxel_downsample_impl(b3d_ctx* c, const float* xyz, size_t n, const float* c
                           size_t capacity, size_t* out_n);
 int estimate_normals_impl(b3d_ctx* c, const float* xyz, size_t n, int k, float* out_normals);
 int compute_fpfh_impl(b3d_ctx* c, const float* xyz, const float* normals, size_t n, float radius, float* out_desc);
+int depth_to_cloud_impl(b3d_ctx* c, const uint16_t* depth, int w, int h, const uint8_t* mask, float scale, float clip,
+                        float fx, float fy, float cx, float cy, const uint8_t* bgr, float* out_xyz, float* out_rgb, size_t capacity, size_t* out_n);
+int register_depth_impl(b3d_ctx* c, const uint16_t* depth, int w, int h, const uint8_t* mask, float scale, float clip, float fx, float fy,
+                        float cx, float cy, float voxel, int k, float radius, int ransac_iterations, float confidence, float icp_threshold,
+                        int icp_iterations, int point_to_plane, b3d_scene_result* out);
 int prepare_model_impl(b3d_ctx* c, const float* xyz, size_t n, float voxel, int k, float radius, size_t* out_n);
 int register_scene_impl(b3d_ctx* c, const float* xyz, size_t n, float voxel, int k, float radius, int ransac_iterations, float confidence,
                         float icp_threshold, int icp_iterations, int point_to_plane, b3d_scene_result* out);

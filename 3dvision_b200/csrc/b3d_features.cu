@@ -33,7 +33,8 @@ namespace b3d {
 
 // fbuf slots
 enum { F_PTS4 = 0, F_NRM4, F_SLOTS, F_GP, F_SORTED, F_PT_SLOT, F_PT_RANK, F_COV, F_OUT, F_NBR, F_NBR_CNT, F_SPFH,
-       F_KEYS_A, F_KEYS_B, F_IDX_A, F_IDX_B, F_CUB, F_SEG, F_VOX_MEAN, F_VOX_COL, F_VOX_KEY, F_VOX_FIRST, F_VOX_ORDER, F_PERM, F_RAW, F_RAW2, F_ORD_OPEN, F_ORD_KEYS, F_ORD_SEQ, F_PIPE_NRM };
+       F_KEYS_A, F_KEYS_B, F_IDX_A, F_IDX_B, F_CUB, F_SEG, F_VOX_MEAN, F_VOX_COL, F_VOX_KEY, F_VOX_FIRST, F_VOX_ORDER, F_PERM, F_RAW, F_RAW2, F_ORD_OPEN, F_ORD_KEYS, F_ORD_SEQ, F_PIPE_NRM, F_IMG_DEPTH, F_IMG_MASK, F_IMG_BGR, F_IMG_XYZ, F_IMG_RGB, F_COUNT };
+static_assert(F_COUNT <= b3d_ctx::kFeatureBufs, "grow b3d_ctx::fbuf");
 
 constexpr int kFeatWarps = 8;                 // warps (= queries in flight) per block
 constexpr int kKeyBuf = 256;                  // per-warp key buffer: sorted prefix + staged candidates
@@ -753,16 +754,100 @@ int voxel_downsample_impl(b3d_ctx* c, const float* xyz, size_t n_, const float* 
 }
 
 // ---------------------------------------------------------------------------------
+// depth image -> instance cloud (pipeline.cpp:38-84, CPU-branch semantics)
+// ---------------------------------------------------------------------------------
+struct DepthImage {
+    const unsigned short* depth; const unsigned char* mask; const unsigned char* bgr;
+    int w; double inv_scale; float clip, fx, fy, cx, cy;
+    __device__ float z_at(unsigned px) const {
+        float z = (float)((double)depth[px] * inv_scale);                           // convertTo(CV_32FC1, 1.0 / scale_to_meters)
+        if (mask && !(mask[px] > 10)) z = 0.0f;                                     // threshold(mask, 10) ; setTo(0, mask == 0)
+        return z;
+    }
+};
+struct PixelKept {
+    DepthImage im;
+    __device__ unsigned operator()(unsigned px) const { const float z = im.z_at(px); return (z <= 0.0f || z > im.clip) ? 0u : 1u; }
+};
+struct PixelEmit {                       // stable compaction: output order is the reference's raster order
+    DepthImage im; float* xyz; float* rgb;
+    __device__ void operator()(unsigned px, unsigned prefix, unsigned flag) const {
+        if (!flag) return;
+        const float z = im.z_at(px);
+        const int u = (int)(px % (unsigned)im.w), v = (int)(px / (unsigned)im.w);
+        xyz[3 * (size_t)prefix] = ((float)u - im.cx) * z / im.fx;
+        xyz[3 * (size_t)prefix + 1] = ((float)v - im.cy) * z / im.fy;
+        xyz[3 * (size_t)prefix + 2] = z;
+        if (rgb) {
+            rgb[3 * (size_t)prefix] = (float)im.bgr[3 * (size_t)px + 2] / 255.0f;
+            rgb[3 * (size_t)prefix + 1] = (float)im.bgr[3 * (size_t)px + 1] / 255.0f;
+            rgb[3 * (size_t)prefix + 2] = (float)im.bgr[3 * (size_t)px] / 255.0f;
+        }
+    }
+};
+
+// device core: host images in, packed xyz (and rgb) left in fbuf[F_IMG_XYZ] / fbuf[F_IMG_RGB]; *n_out points
+static int depth_to_cloud_dev(b3d_ctx* c, const uint16_t* depth, int w, int h, const uint8_t* mask, float scale, float clip,
+                              float fx, float fy, float cx, float cy, const uint8_t* bgr, unsigned* n_out) {
+    const size_t px = (size_t)w * (size_t)h;
+    B3D_CUDA(c, c->fbuf[F_IMG_DEPTH].ensure(px * 2)); B3D_CUDA(c, c->fbuf[F_IMG_XYZ].ensure(px * 12));
+    B3D_CUDA(c, cudaMemcpyAsync(c->fbuf[F_IMG_DEPTH].p, depth, px * 2, cudaMemcpyHostToDevice, c->stream));
+    if (mask) { B3D_CUDA(c, c->fbuf[F_IMG_MASK].ensure(px)); B3D_CUDA(c, cudaMemcpyAsync(c->fbuf[F_IMG_MASK].p, mask, px, cudaMemcpyHostToDevice, c->stream)); }
+    if (bgr) {
+        B3D_CUDA(c, c->fbuf[F_IMG_BGR].ensure(px * 3)); B3D_CUDA(c, c->fbuf[F_IMG_RGB].ensure(px * 12));
+        B3D_CUDA(c, cudaMemcpyAsync(c->fbuf[F_IMG_BGR].p, bgr, px * 3, cudaMemcpyHostToDevice, c->stream));
+    }
+    DepthImage im{c->fbuf[F_IMG_DEPTH].as<unsigned short>(), mask ? c->fbuf[F_IMG_MASK].as<unsigned char>() : nullptr,
+                  bgr ? c->fbuf[F_IMG_BGR].as<unsigned char>() : nullptr, w, 1.0 / (double)scale, clip, fx, fy, cx, cy};
+    PixelKept kept{im}; PixelEmit emit{im, c->fbuf[F_IMG_XYZ].as<float>(), bgr ? c->fbuf[F_IMG_RGB].as<float>() : nullptr};
+    const unsigned tiles = (unsigned)div_up((long long)px, kScanTile);
+    B3D_CUDA(c, c->scan_tmp.ensure(sizeof(unsigned) * (tiles + 2)));
+    unsigned* total = c->scan_tmp.as<unsigned>() + tiles + 1;
+    scan_tile_sums_kernel<<<tiles, kScanThreads, 0, c->stream>>>(kept, (unsigned)px, c->scan_tmp.as<unsigned>());
+    B3D_LAUNCHED(c);
+    scan_tile_offsets_kernel<<<1, kScanThreads, 0, c->stream>>>(c->scan_tmp.as<unsigned>(), tiles, total);
+    B3D_LAUNCHED(c);
+    scan_emit_kernel<<<tiles, kScanThreads, 0, c->stream>>>(kept, emit, (unsigned)px, c->scan_tmp.as<unsigned>());
+    B3D_LAUNCHED(c);
+    B3D_CUDA(c, cudaMemcpyAsync(n_out, total, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+    B3D_CUDA(c, cudaStreamSynchronize(c->stream));
+    return B3D_OK;
+}
+
+int depth_to_cloud_impl(b3d_ctx* c, const uint16_t* depth, int w, int h, const uint8_t* mask, float scale, float clip,
+                        float fx, float fy, float cx, float cy, const uint8_t* bgr, float* out_xyz, float* out_rgb, size_t capacity, size_t* out_n) {
+    *out_n = 0;
+    if (w <= 0 || h <= 0 || (size_t)w * (size_t)h > 0x7FFFFFFFu) return fail(c, B3D_ERR_INVALID, "depth_to_cloud: bad image size");
+    if (!(scale > 0.0f)) return fail(c, B3D_ERR_INVALID, "depth_to_cloud: scale_to_meters must be positive");
+    if (bgr && !out_rgb) return fail(c, B3D_ERR_INVALID, "depth_to_cloud: colour image given but no output for it");
+    unsigned n = 0;
+    int rc = depth_to_cloud_dev(c, depth, w, h, mask, scale, clip, fx, fy, cx, cy, bgr, &n);
+    if (rc != B3D_OK) return rc;
+    *out_n = n;
+    if (n > capacity) return fail(c, B3D_ERR_INVALID, "depth_to_cloud: output capacity too small (out_n holds the size needed)");
+    if (n) {
+        B3D_CUDA(c, cudaMemcpyAsync(out_xyz, c->fbuf[F_IMG_XYZ].p, sizeof(float) * 3 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+        if (bgr) B3D_CUDA(c, cudaMemcpyAsync(out_rgb, c->fbuf[F_IMG_RGB].p, sizeof(float) * 3 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+        B3D_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    return B3D_OK;
+}
+
+// ---------------------------------------------------------------------------------
 // One call per side of a registration, everything resident: raw points in, (points, normals, FPFH) left on the device
 // where the matching / RANSAC / ICP stages read them.  This is the per-instance body of Pipeline::processInstance
 // (src/pipeline.cpp:86-129) without the host containers between the stages.
 // ---------------------------------------------------------------------------------
-static int prepare_cloud_resident(b3d_ctx* c, const float* xyz_host, unsigned n, float voxel, int k, float radius,
+static int prepare_cloud_resident(b3d_ctx* c, const float* xyz, bool on_device, unsigned n, float voxel, int k, float radius,
                                   DevBuf& pts4, DevBuf& nrm4, DevBuf& desc, unsigned* m_out) {
-    B3D_CUDA(c, c->fbuf[F_RAW].ensure(sizeof(float) * 3 * (size_t)n));
-    B3D_CUDA(c, cudaMemcpyAsync(c->fbuf[F_RAW].p, xyz_host, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    const float* d_raw = xyz;
+    if (!on_device) {
+        B3D_CUDA(c, c->fbuf[F_RAW].ensure(sizeof(float) * 3 * (size_t)n));
+        B3D_CUDA(c, cudaMemcpyAsync(c->fbuf[F_RAW].p, xyz, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+        d_raw = c->fbuf[F_RAW].as<float>();
+    }
     float* d_down = nullptr; float* d_unused = nullptr; unsigned m = 0;
-    int rc = voxel_downsample_dev(c, c->fbuf[F_RAW].as<float>(), n, nullptr, voxel, &d_down, &d_unused, &m);
+    int rc = voxel_downsample_dev(c, d_raw, n, nullptr, voxel, &d_down, &d_unused, &m);
     if (rc != B3D_OK) return rc;
     *m_out = m;
     if (m == 0) return B3D_OK;
@@ -782,7 +867,7 @@ int prepare_model_impl(b3d_ctx* c, const float* xyz, size_t n, float voxel, int 
     if (n > 0x7FFFFFFFu) return fail(c, B3D_ERR_INVALID, "prepare_model: too many points");
     c->model_ready = false; c->have_clouds = false; c->have_feats = false; c->have_corr = false; c->prepared = false; c->scored = false;
     unsigned m = 0;
-    if (n) { int rc = prepare_cloud_resident(c, xyz, (unsigned)n, voxel, k, radius, c->tgt4, c->nrm4, c->tdesc, &m); if (rc != B3D_OK) return rc; }
+    if (n) { int rc = prepare_cloud_resident(c, xyz, false, (unsigned)n, voxel, k, radius, c->tgt4, c->nrm4, c->tdesc, &m); if (rc != B3D_OK) return rc; }
     B3D_CUDA(c, cudaStreamSynchronize(c->stream));
     c->n_tgt = m; c->has_normals = m > 0; c->tdesc_p = c->tdesc.as<float>();
     c->model_ready = true;
@@ -790,8 +875,30 @@ int prepare_model_impl(b3d_ctx* c, const float* xyz, size_t n, float voxel, int 
     return B3D_OK;
 }
 
+static int register_resident(b3d_ctx* c, const float* xyz, bool on_device, size_t n, float voxel, int k, float radius, int ransac_iterations,
+                             float confidence, float icp_threshold, int icp_iterations, int point_to_plane, b3d_scene_result* out);
+
 int register_scene_impl(b3d_ctx* c, const float* xyz, size_t n, float voxel, int k, float radius, int ransac_iterations, float confidence,
                         float icp_threshold, int icp_iterations, int point_to_plane, b3d_scene_result* out) {
+    return register_resident(c, xyz, false, n, voxel, k, radius, ransac_iterations, confidence, icp_threshold, icp_iterations, point_to_plane, out);
+}
+
+// depth image + mask of one instance -> pose: Pipeline::processInstance (pipeline.cpp:38-129) up to the refined transform
+int register_depth_impl(b3d_ctx* c, const uint16_t* depth, int w, int h, const uint8_t* mask, float scale, float clip, float fx, float fy,
+                        float cx, float cy, float voxel, int k, float radius, int ransac_iterations, float confidence, float icp_threshold,
+                        int icp_iterations, int point_to_plane, b3d_scene_result* out) {
+    if (!c->model_ready) return fail(c, B3D_ERR_STATE, "register_depth: call b3d_prepare_model first");
+    if (w <= 0 || h <= 0 || (size_t)w * (size_t)h > 0x7FFFFFFFu) return fail(c, B3D_ERR_INVALID, "register_depth: bad image size");
+    if (!(scale > 0.0f)) return fail(c, B3D_ERR_INVALID, "register_depth: scale_to_meters must be positive");
+    unsigned n = 0;
+    int rc = depth_to_cloud_dev(c, depth, w, h, mask, scale, clip, fx, fy, cx, cy, nullptr, &n);
+    if (rc != B3D_OK) return rc;
+    return register_resident(c, c->fbuf[F_IMG_XYZ].as<float>(), true, n, voxel, k, radius, ransac_iterations, confidence, icp_threshold,
+                             icp_iterations, point_to_plane, out);
+}
+
+static int register_resident(b3d_ctx* c, const float* xyz, bool on_device, size_t n, float voxel, int k, float radius, int ransac_iterations,
+                             float confidence, float icp_threshold, int icp_iterations, int point_to_plane, b3d_scene_result* out) {
     if (!c->model_ready) return fail(c, B3D_ERR_STATE, "register_scene: call b3d_prepare_model first");
     if (n > 0x7FFFFFFFu) return fail(c, B3D_ERR_INVALID, "register_scene: too many points");
     for (int i = 0; i < 16; ++i) out->coarse_T[i] = out->T[i] = (i % 5 == 0) ? 1.0f : 0.0f;    // RegistrationResult defaults (registration.hpp:27-29)
@@ -799,7 +906,7 @@ int register_scene_impl(b3d_ctx* c, const float* xyz, size_t n, float voxel, int
     out->coarse_best_iteration = -1; out->icp_iterations = 0; out->n_source_points = 0;
     c->have_clouds = false; c->have_feats = false; c->have_corr = false; c->prepared = false; c->scored = false;
     unsigned m = 0;
-    if (n) { int rc = prepare_cloud_resident(c, xyz, (unsigned)n, voxel, k, radius, c->src4, c->fbuf[F_NRM4], c->sdesc, &m); if (rc != B3D_OK) return rc; }
+    if (n) { int rc = prepare_cloud_resident(c, xyz, on_device, (unsigned)n, voxel, k, radius, c->src4, c->fbuf[F_NRM4], c->sdesc, &m); if (rc != B3D_OK) return rc; }
     out->n_source_points = m;
     c->n_src = m; c->sdesc_p = c->sdesc.as<float>();
     c->have_clouds = true; c->have_feats = true;

@@ -189,6 +189,21 @@ int b3d_register_scene(b3d_ctx* ctx, const float* scene_xyz, size_t n, float vox
                        int ransac_max_iterations, float ransac_confidence, float icp_distance_threshold, int icp_max_iterations,
                        int point_to_plane, b3d_scene_result* out);
 
+/* Depth image of one instance -> cloud: the CPU branch of Pipeline::processInstance, src/pipeline.cpp:38-84 (what
+ * GPUDepth::preprocess + GPUPointCloud::generate, include/gpu_depth.hpp:9-22, do on the reference's GPU branch, but in
+ * the CPU branch's raster order): z = depth / scale_to_meters; zero where mask <= 10 (mask_or_null == NULL: no
+ * masking); keep 0 < z <= clipping_max; x = (u - cx) z / fx, y = (v - cy) z / fy; rgb = bgr reversed / 255.
+ * Mask and colour image must have the depth image's size (the reference's nearest-neighbour mask resize is not done
+ * here).  capacity / out_n as in b3d_voxel_downsample (width*height always suffices). */
+int b3d_depth_to_cloud(b3d_ctx* ctx, const uint16_t* depth, int width, int height, const uint8_t* mask_or_null, float scale_to_meters,
+                       float clipping_max, float fx, float fy, float cx, float cy, const uint8_t* bgr_or_null,
+                       float* out_xyz, float* out_rgb_or_null, size_t capacity, size_t* out_n);
+/* b3d_depth_to_cloud followed by b3d_register_scene without the cloud leaving the device: src/pipeline.cpp:38-129. */
+int b3d_register_depth(b3d_ctx* ctx, const uint16_t* depth, int width, int height, const uint8_t* mask_or_null, float scale_to_meters,
+                       float clipping_max, float fx, float fy, float cx, float cy, float voxel_size, int normals_k, float fpfh_radius,
+                       int ransac_max_iterations, float ransac_confidence, float icp_distance_threshold, int icp_max_iterations,
+                       int point_to_plane, b3d_scene_result* out);
+
 /* Point-to-point accumulation: 0 (default) = add the matched pairs in source order in fp32, exactly
  * as src/registration.cpp:341, 374-386 does (bit-identical sums; one sequential dependency chain per
  * sum, so large clouds cost ~5 cycles per matched point per pass); 1 = deterministic fp64 tree sums

@@ -242,3 +242,18 @@ def compute_fpfh(xyz, normals, radius) -> np.ndarray:
     out = np.empty((xyz.shape[0], 33), np.float32)
     lib().orc_compute_fpfh(_p(xyz), _p(nrm), xyz.shape[0], radius, _p(out))
     return out
+
+
+def depth_to_cloud(depth, mask, scale_to_meters, clipping_max, fx, fy, cx, cy, bgr=None):
+    """pipeline.cpp:38-84, CPU branch. depth uint16 (h,w); mask uint8 (h,w) or None; bgr uint8 (h,w,3) or None."""
+    depth = np.ascontiguousarray(depth, np.uint16); h, w = depth.shape
+    mask = np.ascontiguousarray(mask, np.uint8) if mask is not None else None
+    bgr = np.ascontiguousarray(bgr, np.uint8) if bgr is not None else None
+    xyz = np.empty((h * w, 3), np.float32); rgb = np.empty((h * w, 3), np.float32) if bgr is not None else None
+    f = lib().orc_depth_to_cloud
+    f.restype = C.c_size_t
+    f.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                  C.c_void_p, C.c_void_p, C.c_void_p]
+    n = f(depth.ctypes.data, w, h, mask.ctypes.data if mask is not None else None, scale_to_meters, clipping_max, fx, fy, cx, cy,
+          bgr.ctypes.data if bgr is not None else None, xyz.ctypes.data, rgb.ctypes.data if rgb is not None else None)
+    return xyz[:n].copy(), (rgb[:n].copy() if rgb is not None else None)

@@ -176,6 +176,29 @@ size_t orc_demo_scene_points(int w, int h, float scale_to_meters, float clipping
     return n;
 }
 
+// Mask + scale + deprojection of one instance, CPU branch of Pipeline::processInstance (pipeline.cpp:38-84), for any
+// depth image: convertTo(CV_32FC1, 1/scale); threshold(mask, 10, 255, BINARY) and setTo(0, mask_bool == 0) when a mask is
+// given (apply_mask); skip z <= 0 or z > clipping_max; x = (u - cx) * z / fx; colours bgr -> rgb / 255.  Raster order.
+size_t orc_depth_to_cloud(const uint16_t* depth, int w, int h, const uint8_t* mask_or_null, float scale_to_meters, float clipping_max,
+                          float fx, float fy, float cx, float cy, const uint8_t* bgr_or_null, float* xyz_out, float* rgb_out) {
+    size_t n = 0;
+    for (int v = 0; v < h; ++v) {
+        for (int u = 0; u < w; ++u) {
+            const size_t px = (size_t)v * w + u;
+            float z = (float)((double)depth[px] * (1.0 / (double)scale_to_meters));
+            if (mask_or_null && !(mask_or_null[px] > 10)) z = 0.0f;
+            if (z <= 0 || z > clipping_max) continue;
+            xyz_out[3 * n] = (u - cx) * z / fx; xyz_out[3 * n + 1] = (v - cy) * z / fy; xyz_out[3 * n + 2] = z;
+            if (bgr_or_null && rgb_out) {
+                rgb_out[3 * n] = bgr_or_null[3 * px + 2] / 255.0f; rgb_out[3 * n + 1] = bgr_or_null[3 * px + 1] / 255.0f;
+                rgb_out[3 * n + 2] = bgr_or_null[3 * px] / 255.0f;
+            }
+            ++n;
+        }
+    }
+    return n;
+}
+
 // Dummy model (pipeline.cpp:275-282). Returns count; capacity >= 41*41.
 size_t orc_demo_model_points(float* xyz_out) {
     size_t n = 0;

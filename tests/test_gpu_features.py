@@ -203,3 +203,67 @@ def test_register_scene_requires_a_model(b3d):
             c2.register_scene(np.zeros((10, 3), np.float32), 0.01)
     finally:
         c2.close()
+
+
+# ------------------------------------------------------------------ depth image -> cloud (row f-4)
+def _depth_case(seed, h=240, w=320):
+    rng = np.random.default_rng(seed)
+    depth = rng.integers(0, 2600, (h, w)).astype(np.uint16)
+    depth[rng.random((h, w)) < 0.2] = 0
+    mask = rng.choice(np.array([0, 5, 10, 11, 128, 255], np.uint8), (h, w))
+    bgr = rng.integers(0, 256, (h, w, 3)).astype(np.uint8)
+    return depth, mask, bgr
+
+
+@pytest.mark.parametrize("use_mask,use_bgr", [(True, True), (False, False), (True, False)])
+def test_depth_to_cloud_bit_identical_in_raster_order(ctx, oracle, use_mask, use_bgr):
+    depth, mask, bgr = _depth_case(3)
+    args = (1000.0, 1.5, 611.5, 609.25, 159.5, 121.25)
+    want_xyz, want_rgb = oracle.depth_to_cloud(depth, mask if use_mask else None, *args, bgr=bgr if use_bgr else None)
+    got_xyz, got_rgb = ctx.depth_to_cloud(depth, mask if use_mask else None, *args, bgr=bgr if use_bgr else None)
+    assert same_bits(got_xyz, want_xyz) and want_xyz.shape[0] > 1000
+    assert (got_rgb is None) == (not use_bgr)
+    if use_bgr:
+        assert same_bits(got_rgb, want_rgb)
+
+
+def test_depth_to_cloud_reproduces_the_demo_scene(ctx, oracle):
+    """configs[0]: floor at 1.0 m, 200 x 200 px box at 0.8 m, rectangular mask (pipeline.cpp:211-257) -> the golden's 40401 points."""
+    w, h = 1280, 720
+    u = np.arange(w)[None, :]; v = np.arange(h)[:, None]
+    depth = np.where((np.abs(u - w / 2.0) < 100) & (np.abs(v - h / 2.0) < 100), 800, 1000).astype(np.uint16)
+    mask = (((u >= w // 2 - 100) & (u <= w // 2 + 100) & (v >= h // 2 - 100) & (v <= h // 2 + 100)) * 255).astype(np.uint8)
+    got, _ = ctx.depth_to_cloud(depth, mask, 1000.0, 1.5, 900.0, 900.0, w / 2.0, h / 2.0)
+    want = oracle.demo_scene_points()
+    assert got.shape[0] == json.load(open(GOLDEN))["n_raw_points"] and same_bits(got, want)
+
+
+def test_depth_to_cloud_empty_and_bad_arguments(ctx, b3d):
+    z = np.zeros((8, 8), np.uint16)
+    xyz, _ = ctx.depth_to_cloud(z, None, 1000.0, 1.5, 100.0, 100.0, 4.0, 4.0)
+    assert xyz.shape == (0, 3)
+    with pytest.raises(b3d.B3DError):
+        ctx.depth_to_cloud(z, None, 0.0, 1.5, 100.0, 100.0, 4.0, 4.0)
+
+
+def test_register_depth_equals_deprojection_then_register_scene(b3d):
+    rng = np.random.default_rng(91)
+    voxel = 0.004
+    h, w, f = 300, 400, 500.0
+    uu, vv = np.meshgrid(np.arange(w), np.arange(h))
+    zz = 0.6 + 0.08 * np.sin(uu / 23.0) * np.cos(vv / 17.0) + 0.05 * np.cos((uu + vv) / 31.0) + 0.03 * np.sin(uu / 7.0 + 1.0) * np.sin(vv / 9.0)
+    depth = np.round(zz * 1000.0).astype(np.uint16)
+    mask = np.full((h, w), 255, np.uint8); mask[:20] = 0
+    c2 = b3d.Context(0)
+    try:
+        cloud, _ = c2.depth_to_cloud(depth, mask, 1000.0, 1.5, f, f, w / 2.0, h / 2.0)
+        T = syn.rigid([0.1, 0.3, 0.9], 12.0, [0.02, -0.01, 0.03])
+        model = syn.apply(T, cloud[rng.permutation(cloud.shape[0])[: cloud.shape[0] * 3 // 4]])
+        assert c2.prepare_model(model, voxel) > 1000
+        a = c2.register_scene(cloud, voxel, ransac_max_iterations=5000, icp_max_iterations=30)
+        b = c2.register_depth(depth, mask, 1000.0, 1.5, f, f, w / 2.0, h / 2.0, voxel, ransac_max_iterations=5000, icp_max_iterations=30)
+        assert a["n_source_points"] == b["n_source_points"] > 1000
+        assert np.array_equal(a["coarse"][0], b["coarse"][0]) and np.array_equal(a["refined"][0], b["refined"][0])
+        assert a["refined"][1:] == b["refined"][1:]
+    finally:
+        c2.close()
