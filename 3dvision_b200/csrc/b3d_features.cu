@@ -40,6 +40,7 @@ constexpr int kFeatWarps = 8;                 // warps (= queries in flight) per
 constexpr int kKeyBuf = 256;                  // per-warp key buffer: sorted prefix + staged candidates
 constexpr int kMaxList = 128;                 // longest neighbour list kept (k <= 128; FPFH keeps 100)
 constexpr unsigned long long kNoKey = ~0ull;
+constexpr unsigned kFpfhMaxNn = 100;          // computeFPFH keeps at most 100 neighbours (registration.cpp:139)
 
 // ---------------------------------------------------------------------------------
 // warp-level exact top-K by (d2, index)
@@ -175,6 +176,22 @@ __device__ __forceinline__ void knn_query(WarpList& L, const GridView& g, unsign
 // ---------------------------------------------------------------------------------
 // estimateNormals
 // ---------------------------------------------------------------------------------
+// centroid (3 running sums) and covariance (9 running sums) over the neighbours in list order, one lane per sum
+__device__ __forceinline__ void covariance_in_list_order(const float (*nb)[kMaxList], unsigned kk, unsigned lane, float* __restrict__ cov_out) {
+    const float nf = (float)kk;
+    float c = 0.0f;
+    if (lane < 3) { const float* v = nb[lane]; for (unsigned a = 0; a < kk; ++a) c += v[a]; c /= nf; }   // registration.cpp:111-113
+    const float c0 = __shfl_sync(0xffffffffu, c, 0), c1 = __shfl_sync(0xffffffffu, c, 1), c2 = __shfl_sync(0xffffffffu, c, 2);
+    if (lane < 9) {                                                                // registration.cpp:115-120
+        const unsigned r = lane / 3u, cc = lane % 3u;
+        const float mr = r == 0 ? c0 : (r == 1 ? c1 : c2), mc = cc == 0 ? c0 : (cc == 1 ? c1 : c2);
+        const float* vr = nb[r]; const float* vc = nb[cc];
+        float s = 0.0f;
+        for (unsigned a = 0; a < kk; ++a) { const float dr = vr[a] - mr, dc = vc[a] - mc; s += dr * dc; }
+        cov_out[lane] = s / nf;
+    }
+}
+
 __global__ void __launch_bounds__(kFeatWarps * 32)
 knn_covariance_kernel(const float4* __restrict__ pts, unsigned n, unsigned K, const CellSlot* __restrict__ slots,
                       const float4* __restrict__ sorted, const GridParams* __restrict__ gp, float* __restrict__ cov9) {
@@ -192,18 +209,42 @@ knn_covariance_kernel(const float4* __restrict__ pts, unsigned n, unsigned K, co
             s_nb[warp][0][a] = p.x; s_nb[warp][1][a] = p.y; s_nb[warp][2][a] = p.z;
         }
         __syncwarp();
-        const float nf = (float)kk;
-        float c = 0.0f;
-        if (lane < 3) { const float* v = s_nb[warp][lane]; for (unsigned a = 0; a < kk; ++a) c += v[a]; c /= nf; }   // registration.cpp:111-113
-        const float c0 = __shfl_sync(0xffffffffu, c, 0), c1 = __shfl_sync(0xffffffffu, c, 1), c2 = __shfl_sync(0xffffffffu, c, 2);
-        if (lane < 9) {                                                            // registration.cpp:115-120
-            const unsigned r = lane / 3u, cc = lane % 3u;
-            const float mr = r == 0 ? c0 : (r == 1 ? c1 : c2), mc = cc == 0 ? c0 : (cc == 1 ? c1 : c2);
-            const float* vr = s_nb[warp][r]; const float* vc = s_nb[warp][cc];
-            float s = 0.0f;
-            for (unsigned a = 0; a < kk; ++a) { const float dr = vr[a] - mr, dc = vc[a] - mc; s += dr * dc; }
-            cov9[(size_t)i * 9 + lane] = s / nf;
+        covariance_in_list_order(s_nb[warp], kk, lane, cov9 + (size_t)i * 9);
+        __syncwarp();
+    }
+}
+
+// Fused path: the radius lists computeFPFH needs anyway are sorted by (d2, index) and hold every point within the
+// radius (up to 100), so whenever a list has at least k entries its first k ARE the k nearest neighbours; only points
+// with fewer than k neighbours inside the radius run their own k-NN query (on the same grid).
+__global__ void __launch_bounds__(kFeatWarps * 32)
+list_covariance_kernel(const float4* __restrict__ pts, unsigned n, unsigned K, const unsigned* __restrict__ nbr,
+                       const unsigned* __restrict__ nbr_cnt, const CellSlot* __restrict__ slots, const float4* __restrict__ sorted,
+                       const GridParams* __restrict__ gp, float* __restrict__ cov9) {
+    __shared__ unsigned long long s_keys[kFeatWarps][kKeyBuf];
+    __shared__ float s_nb[kFeatWarps][3][kMaxList];
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const GridView g = make_view(slots, sorted, gp);
+    WarpList L; L.keys = s_keys[warp];
+    for (unsigned i = blockIdx.x * kFeatWarps + warp; i < n; i += gridDim.x * kFeatWarps) {
+        const unsigned cnt = nbr_cnt[i];
+        unsigned kk;
+        if (cnt >= K) {
+            kk = K;
+            for (unsigned a = lane; a < kk; a += 32) {
+                const float4 p = pts[nbr[(size_t)i * kFpfhMaxNn + a]];
+                s_nb[warp][0][a] = p.x; s_nb[warp][1][a] = p.y; s_nb[warp][2][a] = p.z;
+            }
+        } else {
+            knn_query(L, g, n, pts[i], K, lane);
+            kk = L.n_sorted;
+            for (unsigned a = lane; a < kk; a += 32) {
+                const float4 p = pts[(unsigned)L.keys[a]];
+                s_nb[warp][0][a] = p.x; s_nb[warp][1][a] = p.y; s_nb[warp][2][a] = p.z;
+            }
         }
+        __syncwarp();
+        covariance_in_list_order(s_nb[warp], kk, lane, cov9 + (size_t)i * 9);
         __syncwarp();
     }
 }
@@ -225,7 +266,6 @@ __global__ void normal_from_covariance_kernel(const float4* __restrict__ pts, co
 // ---------------------------------------------------------------------------------
 // computeFPFH
 // ---------------------------------------------------------------------------------
-constexpr unsigned kFpfhMaxNn = 100;           // registration.cpp:139
 
 __global__ void __launch_bounds__(kFeatWarps * 32)
 radius_neighbors_kernel(const float4* __restrict__ pts, unsigned n, float r2, const CellSlot* __restrict__ slots,
@@ -609,26 +649,60 @@ int estimate_normals_impl(b3d_ctx* c, const float* xyz, size_t n_, int k, float*
     return B3D_OK;
 }
 
-// device core: pts / nrm (float4, n) -> d_out (n x 33)
-int compute_fpfh_dev(b3d_ctx* c, const float4* pts, const float4* nrm, unsigned n, float radius, float* d_out) {
+// radius lists (shared by the fused normals and by FPFH): grid of cell 1.02 r, then one warp per query
+static int radius_lists_dev(b3d_ctx* c, const float4* pts, unsigned n, float radius, PointGrid* g) {
     if (n > 0x7FFFFFFFu / kFpfhMaxNn) return fail(c, B3D_ERR_INVALID, "compute_fpfh: too many points");
-    StageTimer timer(c, 9);
     const float r2 = radius * radius;                                               // registration.cpp:90
-    PointGrid g;
-    int rc = build_point_grid(c, pts, n, radius * 1.02f, &g);
+    int rc = build_point_grid(c, pts, n, radius * 1.02f, g);
     if (rc != B3D_OK) return rc;
     B3D_CUDA(c, c->fbuf[F_NBR].ensure(sizeof(unsigned) * kFpfhMaxNn * (size_t)n));
     B3D_CUDA(c, c->fbuf[F_NBR_CNT].ensure(sizeof(unsigned) * n));
+    radius_neighbors_kernel<<<grid_for(n, kFeatWarps, 16), kFeatWarps * 32, 0, c->stream>>>(pts, n, r2, g->slots, g->sorted, g->gp,
+                                                                                          c->fbuf[F_NBR].as<unsigned>(), c->fbuf[F_NBR_CNT].as<unsigned>());
+    B3D_LAUNCHED(c);
+    return B3D_OK;
+}
+
+static int fpfh_from_lists_dev(b3d_ctx* c, const float4* pts, const float4* nrm, unsigned n, float* d_out) {
     B3D_CUDA(c, c->fbuf[F_SPFH].ensure(sizeof(float) * 33 * (size_t)n));
     unsigned* nbr = c->fbuf[F_NBR].as<unsigned>(); unsigned* cnt = c->fbuf[F_NBR_CNT].as<unsigned>();
     const int blocks = grid_for(n, kFeatWarps, 16);
-    radius_neighbors_kernel<<<blocks, kFeatWarps * 32, 0, c->stream>>>(pts, n, r2, g.slots, g.sorted, g.gp, nbr, cnt);
-    B3D_LAUNCHED(c);
     spfh_kernel<<<blocks, kFeatWarps * 32, 0, c->stream>>>(pts, nrm, n, nbr, cnt, c->fbuf[F_SPFH].as<float>());
     B3D_LAUNCHED(c);
     fpfh_kernel<<<blocks, kFeatWarps * 32, 0, c->stream>>>(pts, n, nbr, cnt, c->fbuf[F_SPFH].as<float>(), d_out);
     B3D_LAUNCHED(c);
     return B3D_OK;
+}
+
+// device core: pts / nrm (float4, n) -> d_out (n x 33)
+int compute_fpfh_dev(b3d_ctx* c, const float4* pts, const float4* nrm, unsigned n, float radius, float* d_out) {
+    StageTimer timer(c, 9);
+    PointGrid g;
+    int rc = radius_lists_dev(c, pts, n, radius, &g);
+    if (rc != B3D_OK) return rc;
+    return fpfh_from_lists_dev(c, pts, nrm, n, d_out);
+}
+
+// fused: normals (k-NN taken from the radius lists) and FPFH from one neighbour search
+static int normals_and_fpfh_dev(b3d_ctx* c, const float4* pts, unsigned n, int k, float radius, float* d_nrm_xyz, float4* nrm4, float* d_desc) {
+    if (k < 1 || k > kMaxList) return fail(c, B3D_ERR_INVALID, "estimate_normals: k must be in [1, 128]");
+    const unsigned K = (unsigned)k < n ? (unsigned)k : n;
+    PointGrid g;
+    {
+        StageTimer timer(c, 8);
+        int rc = radius_lists_dev(c, pts, n, radius, &g);
+        if (rc != B3D_OK) return rc;
+        B3D_CUDA(c, c->fbuf[F_COV].ensure(sizeof(float) * 9 * n));
+        list_covariance_kernel<<<grid_for(n, kFeatWarps, 16), kFeatWarps * 32, 0, c->stream>>>(pts, n, K, c->fbuf[F_NBR].as<unsigned>(),
+            c->fbuf[F_NBR_CNT].as<unsigned>(), g.slots, g.sorted, g.gp, c->fbuf[F_COV].as<float>());
+        B3D_LAUNCHED(c);
+        normal_from_covariance_kernel<<<div_up(n, 128), 128, 0, c->stream>>>(pts, c->fbuf[F_COV].as<float>(), n, d_nrm_xyz);
+        B3D_LAUNCHED(c);
+        rc = xyz_to_float4(c, d_nrm_xyz, n, nrm4);
+        if (rc != B3D_OK) return rc;
+    }
+    StageTimer timer(c, 9);
+    return fpfh_from_lists_dev(c, pts, nrm4, n, d_desc);
 }
 
 int compute_fpfh_impl(b3d_ctx* c, const float* xyz, const float* normals, size_t n_, float radius, float* out_desc) {
@@ -856,11 +930,7 @@ static int prepare_cloud_resident(b3d_ctx* c, const float* xyz, bool on_device, 
     B3D_CUDA(c, c->fbuf[F_PIPE_NRM].ensure(sizeof(float) * 3 * (size_t)m));
     rc = xyz_to_float4(c, d_down, m, pts4.as<float4>());
     if (rc != B3D_OK) return rc;
-    rc = estimate_normals_dev(c, pts4.as<float4>(), m, k, c->fbuf[F_PIPE_NRM].as<float>());
-    if (rc != B3D_OK) return rc;
-    rc = xyz_to_float4(c, c->fbuf[F_PIPE_NRM].as<float>(), m, nrm4.as<float4>());
-    if (rc != B3D_OK) return rc;
-    return compute_fpfh_dev(c, pts4.as<float4>(), nrm4.as<float4>(), m, radius, desc.as<float>());
+    return normals_and_fpfh_dev(c, pts4.as<float4>(), m, k, radius, c->fbuf[F_PIPE_NRM].as<float>(), nrm4.as<float4>(), desc.as<float>());
 }
 
 int prepare_model_impl(b3d_ctx* c, const float* xyz, size_t n, float voxel, int k, float radius, size_t* out_n) {

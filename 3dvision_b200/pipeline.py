@@ -19,6 +19,8 @@ import threading
 from concurrent.futures import ThreadPoolExecutor
 from dataclasses import dataclass
 
+import numpy as np
+
 from .registration import (FPFHFeatures, GPURegistration, PointCloud, Registration, RegistrationResult)
 
 
@@ -49,6 +51,37 @@ def process_instance(inst: Instance) -> tuple[RegistrationResult, RegistrationRe
         fine = Registration.icpRefine(inst.source, inst.target, coarse.transformation, thr, inst.icp_iterations,
                                       inst.use_point_to_plane)
     return coarse, fine
+
+
+def world_pose(refined_transformation, camera_extrinsics=None):
+    """pipeline.cpp:136-137: T_camera_object = refined^-1; T_world_object = extrinsics * T_camera_object.
+    Orchestrator-side 4x4 algebra on the host (O(1) per instance, not a device stage); float32 like the reference, but
+    Eigen's 4x4 inverse kernel is not restated, so the last bits may differ from the reference's."""
+    Tco = np.linalg.inv(np.asarray(refined_transformation, np.float32)).astype(np.float32)
+    if camera_extrinsics is None:
+        return Tco
+    return (np.asarray(camera_extrinsics, np.float32) @ Tco).astype(np.float32)
+
+
+def filter_duplicates(waypoints, min_distance: float):
+    """Pipeline::filterDuplicates (pipeline.cpp:153-180): greedy de-duplication of the per-instance poses by the distance
+    between their translations; of two poses closer than min_distance the one nearer the origin is kept, in the slot of
+    the first."""
+    kept = []
+    for wp in waypoints:
+        wp = np.asarray(wp, np.float32)
+        pos = wp[:3, 3]
+        dup = False
+        for i, other in enumerate(kept):
+            d = pos - other[:3, 3]
+            if np.float32(np.sqrt(np.float32(d[0] * d[0] + np.float32(d[1] * d[1] + d[2] * d[2])))) < np.float32(min_distance):
+                dup = True
+                if np.linalg.norm(pos) < np.linalg.norm(other[:3, 3]):
+                    kept[i] = wp
+                break
+        if not dup:
+            kept.append(wp)
+    return kept
 
 
 _pools: dict[int, ThreadPoolExecutor] = {}
