@@ -60,12 +60,17 @@ using namespace b3d;
 extern "C" {
 
 int b3d_cuda_available(void) {
+    // The orchestrator asks before every instance (src/pipeline.cpp:107) and cudaGetDeviceProperties costs milliseconds,
+    // so a positive answer is remembered for the process; a negative one is re-probed (a device may appear later).
+    static int cached = 0;
+    if (cached) return 1;
     if (!device_usable()) return 0;
-    cudaDeviceProp prop;
-    int dev = 0;
+    int dev = 0, major = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return 0; }
-    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) { cudaGetLastError(); return 0; }
-    return prop.major == 10 ? 1 : 0;        // the library carries sm_100a code only
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) { cudaGetLastError(); return 0; }
+    if (major != 10) return 0;              // the library carries sm_100a code only
+    cached = 1;
+    return 1;
 }
 
 const char* b3d_strerror(int status) {
@@ -93,6 +98,14 @@ int b3d_ctx_create(int device, b3d_ctx** out) {
     c->device = device;
     if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return B3D_ERR_CUDA; }
     c->stream = c->own_stream;
+    {   // keep freed workspace in the device's default pool instead of returning it to the driver at every sync
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        } else cudaGetLastError();
+    }
+    alloc_stream_valid() = false;
     if (c->state.ensure(sizeof(DeviceState)) != cudaSuccess ||
         cudaMallocHost(&c->h_state, sizeof(DeviceState)) != cudaSuccess) { b3d_ctx_destroy(c); return B3D_ERR_ALLOC; }
     cudaMemsetAsync(c->state.p, 0, sizeof(DeviceState), c->stream);
@@ -105,11 +118,13 @@ int b3d_ctx_create(int device, b3d_ctx** out) {
 void b3d_ctx_destroy(b3d_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
+    alloc_stream_valid() = false;
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->own_stream && c->own_stream != c->stream) cudaStreamSynchronize(c->own_stream);
     DevBuf* bufs[] = {&c->stage_a, &c->stage_b, &c->stage_c, &c->src4, &c->tgt4, &c->nrm4, &c->sdesc, &c->tdesc, &c->corr, &c->raw,
                       &c->draws, &c->scan_tmp, &c->hyp, &c->counts, &c->pairs, &c->seqsum, &c->grid_slots, &c->grid_cursor,
                       &c->grid_pts, &c->grid_nrm, &c->pt_slot, &c->pt_rank, &c->partials, &c->nn_idx, &c->nn_d2, &c->state,
-                      &c->seq_rec, &c->seq_match, &c->seq_P, &c->seq_Q, &c->seq_N, &c->fine_slots, &c->fine_pts, &c->bail_list_a, &c->bail_list_b, &c->bail_state, &c->src_slots, &c->src_sorted, &c->src_slot, &c->src_rank,
+                      &c->seq_rec, &c->seq_match, &c->seq_P, &c->seq_Q, &c->seq_N, &c->fine_slots, &c->fine_pts, &c->nbh_slot27, &c->nbh_cursor, &c->bail_list_a, &c->bail_list_b, &c->bail_state, &c->src_slots, &c->src_sorted, &c->src_slot, &c->src_rank,
                       &c->tc_a_tiles, &c->tc_b_tiles, &c->tc_norm2, &c->tc_best, &c->tc_aux};
     for (DevBuf* b : bufs) b->release();
     for (DevBuf& b : c->fbuf) b.release();
@@ -121,7 +136,7 @@ void b3d_ctx_destroy(b3d_ctx* c) {
 
 int b3d_ctx_set_stream(b3d_ctx* c, void* cuda_stream) {
     if (!c) return B3D_ERR_INVALID;
-    B3D_CUDA(c, cudaSetDevice(c->device));
+    B3D_CUDA(c, enter(c));
     B3D_CUDA(c, cudaStreamSynchronize(c->stream));
     c->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : c->own_stream;
     return B3D_OK;
@@ -139,7 +154,7 @@ float b3d_stage_ms(const b3d_ctx* c, int stage) {
 
 int b3d_measure_fp32_rate(b3d_ctx* c, double* out_ops_per_second) {
     if (!c || !out_ops_per_second) return B3D_ERR_INVALID;
-    B3D_CUDA(c, cudaSetDevice(c->device));
+    B3D_CUDA(c, enter(c));
     B3D_CUDA(c, c->seqsum.ensure(64));
     const int iters = 1 << 14, blocks = kNumSMs * 8, threads = 256;
     cudaEvent_t e0, e1;
@@ -166,7 +181,7 @@ int b3d_set_clouds(b3d_ctx* c, const float* src_xyz, size_t n_src, const float* 
     if (!c) return B3D_ERR_INVALID;
     if ((n_src && !src_xyz) || (n_tgt && !tgt_xyz)) return fail(c, B3D_ERR_INVALID, "set_clouds: null cloud pointer");
     if (n_src >= 0xFFFFFFFFull || n_tgt >= 0xFFFFFFFFull) return fail(c, B3D_ERR_INVALID, "set_clouds: more than 2^32-2 points");
-    B3D_CUDA(c, cudaSetDevice(c->device));
+    B3D_CUDA(c, enter(c));
     c->have_clouds = false; c->have_corr = false; c->prepared = false; c->scored = false; c->model_ready = false;
     int rc = upload_cloud(c, src_xyz, n_src, on_device, c->stage_a, c->src4); if (rc) return rc;
     rc = upload_cloud(c, tgt_xyz, n_tgt, on_device, c->stage_b, c->tgt4); if (rc) return rc;
@@ -181,7 +196,7 @@ int b3d_set_features(b3d_ctx* c, const float* src_desc, const float* tgt_desc, i
     if (!c) return B3D_ERR_INVALID;
     if (!c->have_clouds) return fail(c, B3D_ERR_STATE, "set_features: call set_clouds first");
     if ((c->n_src && !src_desc) || (c->n_tgt && !tgt_desc)) return fail(c, B3D_ERR_INVALID, "set_features: null descriptor pointer");
-    B3D_CUDA(c, cudaSetDevice(c->device));
+    B3D_CUDA(c, enter(c));
     c->have_feats = false;
     if (on_device) { c->sdesc_p = src_desc; c->tdesc_p = tgt_desc; }
     else {
@@ -203,7 +218,7 @@ int b3d_set_match_mode(b3d_ctx* c, int mode) {
 
 int b3d_score_recounts(b3d_ctx* c, uint64_t* out) {
     if (!c || !out) return B3D_ERR_INVALID;
-    B3D_CUDA(c, cudaSetDevice(c->device));
+    B3D_CUDA(c, enter(c));
     unsigned long long v = 0;
     B3D_CUDA(c, cudaMemcpyAsync(&v, &c->state.as<DeviceState>()->score_recounts, sizeof(v), cudaMemcpyDeviceToHost, c->stream));
     B3D_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -214,13 +229,13 @@ int b3d_score_recounts(b3d_ctx* c, uint64_t* out) {
 int b3d_voxel_downsample(b3d_ctx* c, const float* xyz, size_t n, const float* colors_or_null, float voxel_size,
                          float* out_xyz, float* out_colors_or_null, size_t capacity, size_t* out_n) {
     if (!c || !out_n || (n && (!xyz || !out_xyz))) return B3D_ERR_INVALID;
-    B3D_CUDA(c, cudaSetDevice(c->device));
+    B3D_CUDA(c, enter(c));
     return voxel_downsample_impl(c, xyz, n, colors_or_null, voxel_size, out_xyz, out_colors_or_null, capacity, out_n);
 }
 
 int b3d_prepare_model(b3d_ctx* c, const float* model_xyz, size_t n, float voxel_size, int normals_k, float fpfh_radius, size_t* out_n_points) {
     if (!c || (n && !model_xyz)) return B3D_ERR_INVALID;
-    B3D_CUDA(c, cudaSetDevice(c->device));
+    B3D_CUDA(c, enter(c));
     return prepare_model_impl(c, model_xyz, n, voxel_size, normals_k, fpfh_radius, out_n_points);
 }
 
@@ -228,7 +243,7 @@ int b3d_register_scene(b3d_ctx* c, const float* scene_xyz, size_t n, float voxel
                        int ransac_max_iterations, float ransac_confidence, float icp_distance_threshold, int icp_max_iterations,
                        int point_to_plane, b3d_scene_result* out) {
     if (!c || !out || (n && !scene_xyz)) return B3D_ERR_INVALID;
-    B3D_CUDA(c, cudaSetDevice(c->device));
+    B3D_CUDA(c, enter(c));
     return register_scene_impl(c, scene_xyz, n, voxel_size, normals_k, fpfh_radius, ransac_max_iterations, ransac_confidence,
                                icp_distance_threshold, icp_max_iterations, point_to_plane, out);
 }
@@ -237,7 +252,7 @@ int b3d_depth_to_cloud(b3d_ctx* c, const uint16_t* depth, int width, int height,
                        float clipping_max, float fx, float fy, float cx, float cy, const uint8_t* bgr_or_null,
                        float* out_xyz, float* out_rgb_or_null, size_t capacity, size_t* out_n) {
     if (!c || !depth || !out_xyz || !out_n) return B3D_ERR_INVALID;
-    B3D_CUDA(c, cudaSetDevice(c->device));
+    B3D_CUDA(c, enter(c));
     return depth_to_cloud_impl(c, depth, width, height, mask_or_null, scale_to_meters, clipping_max, fx, fy, cx, cy, bgr_or_null,
                                out_xyz, out_rgb_or_null, capacity, out_n);
 }
@@ -247,7 +262,7 @@ int b3d_register_depth(b3d_ctx* c, const uint16_t* depth, int width, int height,
                        int ransac_max_iterations, float ransac_confidence, float icp_distance_threshold, int icp_max_iterations,
                        int point_to_plane, b3d_scene_result* out) {
     if (!c || !depth || !out) return B3D_ERR_INVALID;
-    B3D_CUDA(c, cudaSetDevice(c->device));
+    B3D_CUDA(c, enter(c));
     return register_depth_impl(c, depth, width, height, mask_or_null, scale_to_meters, clipping_max, fx, fy, cx, cy, voxel_size, normals_k,
                                fpfh_radius, ransac_max_iterations, ransac_confidence, icp_distance_threshold, icp_max_iterations,
                                point_to_plane, out);
@@ -261,13 +276,13 @@ int b3d_set_voxel_order_mode(b3d_ctx* c, int mode) {
 
 int b3d_estimate_normals(b3d_ctx* c, const float* xyz, size_t n, int k, float* out_normals) {
     if (!c || (n && (!xyz || !out_normals))) return B3D_ERR_INVALID;
-    B3D_CUDA(c, cudaSetDevice(c->device));
+    B3D_CUDA(c, enter(c));
     return estimate_normals_impl(c, xyz, n, k, out_normals);
 }
 
 int b3d_compute_fpfh(b3d_ctx* c, const float* xyz, const float* normals, size_t n, float radius, float* out_desc) {
     if (!c || (n && (!xyz || !normals || !out_desc))) return B3D_ERR_INVALID;
-    B3D_CUDA(c, cudaSetDevice(c->device));
+    B3D_CUDA(c, enter(c));
     return compute_fpfh_impl(c, xyz, normals, n, radius, out_desc);
 }
 
@@ -285,7 +300,7 @@ int b3d_set_score_mode(b3d_ctx* c, int mode) {
 
 int b3d_match_features(b3d_ctx* c, size_t row0, size_t row1) {
     if (!c) return B3D_ERR_INVALID;
-    B3D_CUDA(c, cudaSetDevice(c->device));
+    B3D_CUDA(c, enter(c));
     int rc = match_features_impl(c, row0, row1);
     if (rc == B3D_OK && row0 == 0 && row1 == c->n_src) c->have_corr = true;
     return rc;
@@ -294,7 +309,7 @@ int b3d_match_features(b3d_ctx* c, size_t row0, size_t row1) {
 int b3d_get_correspondences(b3d_ctx* c, uint32_t* out_host) {
     if (!c || !out_host) return B3D_ERR_INVALID;
     if (!c->have_clouds || c->corr.cap < sizeof(uint32_t) * c->n_src) return fail(c, B3D_ERR_STATE, "get_correspondences: none computed");
-    B3D_CUDA(c, cudaSetDevice(c->device));
+    B3D_CUDA(c, enter(c));
     if (c->n_src) B3D_CUDA(c, cudaMemcpyAsync(out_host, c->corr.p, sizeof(uint32_t) * c->n_src, cudaMemcpyDeviceToHost, c->stream));
     B3D_CUDA(c, cudaStreamSynchronize(c->stream));
     return B3D_OK;
@@ -303,7 +318,7 @@ int b3d_get_correspondences(b3d_ctx* c, uint32_t* out_host) {
 int b3d_get_correspondences_dev(b3d_ctx* c, uint32_t* out_dev) {
     if (!c || !out_dev) return B3D_ERR_INVALID;
     if (!c->have_clouds || c->corr.cap < sizeof(uint32_t) * c->n_src) return fail(c, B3D_ERR_STATE, "get_correspondences_dev: none computed");
-    B3D_CUDA(c, cudaSetDevice(c->device));
+    B3D_CUDA(c, enter(c));
     if (c->n_src) B3D_CUDA(c, cudaMemcpyAsync(out_dev, c->corr.p, sizeof(uint32_t) * c->n_src, cudaMemcpyDeviceToDevice, c->stream));
     return B3D_OK;
 }
@@ -311,7 +326,7 @@ int b3d_get_correspondences_dev(b3d_ctx* c, uint32_t* out_dev) {
 int b3d_set_correspondences(b3d_ctx* c, const uint32_t* corr, int on_device) {
     if (!c) return B3D_ERR_INVALID;
     if (!c->have_clouds) return fail(c, B3D_ERR_STATE, "set_correspondences: call set_clouds first");
-    B3D_CUDA(c, cudaSetDevice(c->device));
+    B3D_CUDA(c, enter(c));
     B3D_CUDA(c, c->corr.ensure(sizeof(uint32_t) * (c->n_src ? c->n_src : 1)));
     if (corr && c->n_src && corr != c->corr.as<uint32_t>())
         B3D_CUDA(c, cudaMemcpyAsync(c->corr.p, corr, sizeof(uint32_t) * c->n_src, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
@@ -322,7 +337,7 @@ int b3d_set_correspondences(b3d_ctx* c, const uint32_t* corr, int on_device) {
 int b3d_correspondences_devptr(b3d_ctx* c, void** out) {
     if (!c || !out) return B3D_ERR_INVALID;
     if (!c->have_clouds) return fail(c, B3D_ERR_STATE, "correspondences_devptr: call set_clouds first");
-    B3D_CUDA(c, cudaSetDevice(c->device));
+    B3D_CUDA(c, enter(c));
     B3D_CUDA(c, c->corr.ensure(sizeof(uint32_t) * (c->n_src ? c->n_src : 1)));
     *out = c->corr.p;
     return B3D_OK;
@@ -330,22 +345,22 @@ int b3d_correspondences_devptr(b3d_ctx* c, void** out) {
 
 int b3d_ransac_prepare(b3d_ctx* c, float voxel, int max_iterations, float confidence) {
     if (!c) return B3D_ERR_INVALID;
-    B3D_CUDA(c, cudaSetDevice(c->device));
+    B3D_CUDA(c, enter(c));
     return ransac_prepare_impl(c, voxel, max_iterations, confidence);
 }
 int b3d_ransac_score(b3d_ctx* c, int h0, int h1) {
     if (!c) return B3D_ERR_INVALID;
-    B3D_CUDA(c, cudaSetDevice(c->device));
+    B3D_CUDA(c, enter(c));
     return ransac_score_impl(c, h0, h1);
 }
 int b3d_ransac_reduce(b3d_ctx* c, int h0, int h1, const int64_t* limit_key_dev, int64_t* keys_dev) {
     if (!c) return B3D_ERR_INVALID;
-    B3D_CUDA(c, cudaSetDevice(c->device));
+    B3D_CUDA(c, enter(c));
     return ransac_reduce_impl(c, h0, h1, limit_key_dev, keys_dev);
 }
 int b3d_ransac_finish(b3d_ctx* c, const int64_t* keys_dev, float* T, float* fitness, float* rmse, int32_t* best) {
     if (!c || !T || !fitness || !rmse) return B3D_ERR_INVALID;
-    B3D_CUDA(c, cudaSetDevice(c->device));
+    B3D_CUDA(c, enter(c));
     return ransac_finish_impl(c, keys_dev, T, fitness, rmse, best);
 }
 
@@ -353,7 +368,7 @@ int b3d_ransac_counts(b3d_ctx* c, int h0, int h1, int32_t* out_host) {
     if (!c || !out_host) return B3D_ERR_INVALID;
     if (!c->prepared) return fail(c, B3D_ERR_STATE, "ransac_counts: not prepared");
     if (h0 < 0 || h1 > c->H || h0 > h1) return fail(c, B3D_ERR_INVALID, "ransac_counts: bad range");
-    B3D_CUDA(c, cudaSetDevice(c->device));
+    B3D_CUDA(c, enter(c));
     { int rc = ransac_generate_impl(c, h0, h1); if (rc != B3D_OK) return rc; }   // degenerate-triple flags need the hypotheses
     if (h1 > h0 && c->n_src) B3D_CUDA(c, cudaMemcpyAsync(out_host, c->counts.as<int>() + h0, sizeof(int) * (size_t)(h1 - h0), cudaMemcpyDeviceToHost, c->stream));
     B3D_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -369,7 +384,7 @@ int b3d_ransac_hypotheses(b3d_ctx* c, int h0, int h1, float* out_host) {
     if (!c || !out_host) return B3D_ERR_INVALID;
     if (!c->prepared) return fail(c, B3D_ERR_STATE, "ransac_hypotheses: not prepared");
     if (h0 < 0 || h1 > c->H || h0 > h1) return fail(c, B3D_ERR_INVALID, "ransac_hypotheses: bad range");
-    B3D_CUDA(c, cudaSetDevice(c->device));
+    B3D_CUDA(c, enter(c));
     if (h1 == h0 || c->n_src == 0) return B3D_OK;
     { int rc = ransac_generate_impl(c, h0, h1); if (rc != B3D_OK) return rc; }
     const size_t n = (size_t)(h1 - h0);
@@ -387,13 +402,13 @@ int b3d_ransac_hypotheses(b3d_ctx* c, int h0, int h1, float* out_host) {
 int b3d_icp_run(b3d_ctx* c, const float* T0, float thr, int max_iter, int p2plane, int stop_on_conv,
                 float* T, float* fitness, float* rmse, int32_t* iters) {
     if (!c || !T0 || !T || !fitness || !rmse) return B3D_ERR_INVALID;
-    B3D_CUDA(c, cudaSetDevice(c->device));
+    B3D_CUDA(c, enter(c));
     return icp_run_impl(c, T0, thr, max_iter, p2plane, stop_on_conv, T, fitness, rmse, iters);
 }
 
 int b3d_icp_nearest(b3d_ctx* c, const float* T, float thr, uint32_t* idx_host, float* d2_host) {
     if (!c || !T || !idx_host || !d2_host) return B3D_ERR_INVALID;
-    B3D_CUDA(c, cudaSetDevice(c->device));
+    B3D_CUDA(c, enter(c));
     return icp_nearest_impl(c, T, thr, idx_host, d2_host);
 }
 

@@ -33,6 +33,8 @@ struct GridParams {
     unsigned occupied;          // cells in use (counted while inserting)
     unsigned enabled;           // fine grid only: 0 when it would not pay off
     float accept2;              // fine grid only: a match closer than sqrt(accept2) is provably the global nearest
+    unsigned complete;          // fine level only: its cell is the coarse cell, so its lists hold every match the reference keeps
+    unsigned overflow;          // fine level only: 1 if its neighbourhood table filled up (level unusable for this call)
 };
 
 __device__ __forceinline__ int cell_coord(float v, float inv_cell) {

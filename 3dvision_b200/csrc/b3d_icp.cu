@@ -110,34 +110,114 @@ __global__ void fine_params_kernel(const GridParams* __restrict__ gc, GridParams
     float cell = 2.0f * gc->cell / sqrtf(fmaxf(ppc, 1.0f));
     cell = fmaxf(cell, gc->cell * (1.0f / 16.0f));
     cell = fmaxf(cell, max_abs * (1.0001f / kCoordLimit));
-    const bool on = isfinite(cell) && cell > 0.0f && cell < 0.6f * gc->cell && n >= 4096u;
-    gf->inv_cell = on ? 1.0f / cell : 0.0f;
-    gf->cell = on ? 1.0f / gf->inv_cell : 0.0f;
+    const bool usable = isfinite(gc->cell) && gc->cell > 0.0f && gc->inv_cell > 0.0f;
+    const bool finer = usable && isfinite(cell) && cell > 0.0f && cell < 0.6f * gc->cell;
+    // sparse target: lists over the coarse cells themselves.  They hold every point of the 27 coarse cells, i.e. every
+    // match the reference can keep, so the lookup is complete and the coarse walk is never needed.
+    gf->inv_cell = finer ? 1.0f / cell : (usable ? gc->inv_cell : 0.0f);
+    gf->cell = finer ? 1.0f / gf->inv_cell : (usable ? gc->cell : 0.0f);
     gf->slack = gc->slack;
     gf->mask = capacity - 1u;
     gf->max_abs_bits = gc->max_abs_bits;
     gf->n_points = n;
-    gf->enabled = on ? 1u : 0u;
+    gf->enabled = usable ? 1u : 0u;
+    gf->complete = (usable && !finer) ? 1u : 0u;
     const float reach = gf->cell * 0.98f - gf->slack;          // every target closer than this lies in the 27 fine cells
-    gf->accept2 = (on && reach > 0.0f) ? __fmul_rd(reach, reach) * 0.999f : 0.0f;
+    gf->accept2 = (finer && reach > 0.0f) ? __fmul_rd(reach, reach) * 0.999f : 0.0f;
+}
+
+// Second level = per-cell NEIGHBOURHOOD LISTS.  Walking 27 hash cells per query is 27 dependent L2 round trips and
+// leaves ~10 of 32 lanes active; measured, a query that probes ONE cell and scans one contiguous run costs a third
+// (configs[1]: 94 -> 34 us per iteration with an own-cell-only probe).  So the 27-cell union is materialised once per
+// call: every target point is appended to the list of each of the 27 fine cells around it (count with atomics, scan,
+// scatter), 27*n float4 in total; a query then probes the table with its own cell and scans that list.  The list of
+// cell c holds exactly the points of the 27 cells around c, so the acceptance rule is unchanged: a lexicographic
+// (d2, index) minimum closer than the fine reach is the global one.  A cell without a list has no point within the
+// reach.  If the table fills up (very sparse targets) the level is flagged unusable and every query takes the coarse walk.
+constexpr int kNeighbourhoodProbes = 256;
+__device__ __forceinline__ unsigned neighbourhood_claim(CellSlot* __restrict__ slots, unsigned mask, unsigned long long key) {
+    unsigned slot = hash_cell(key) & mask;
+    for (int probe = 0; probe < kNeighbourhoodProbes / 2; ++probe) {
+        const unsigned long long prev = atomicCAS(&slots[slot].key, kEmptyKey, key);
+        if (prev == kEmptyKey || prev == key) return slot;
+        slot = (slot + 1u) & mask;
+    }
+    return 0xFFFFFFFFu;
+}
+__global__ void neighbourhood_count_kernel(const float4* __restrict__ pts, unsigned n, CellSlot* __restrict__ slots, GridParams* __restrict__ gf,
+                                           unsigned* __restrict__ pt_slot27) {
+    if (!gf->enabled) return;
+    const float inv = gf->inv_cell;
+    const unsigned mask = gf->mask;
+    for (size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x; w < (size_t)n * 27u; w += (size_t)gridDim.x * blockDim.x) {
+        const unsigned i = (unsigned)(w / 27u), k = (unsigned)(w % 27u);
+        const float4 p = pts[i];
+        const unsigned long long key = pack_cell(cell_coord(p.x, inv) + (int)(k % 3u) - 1, cell_coord(p.y, inv) + (int)((k / 3u) % 3u) - 1,
+                                                 cell_coord(p.z, inv) + (int)(k / 9u) - 1);
+        const unsigned slot = neighbourhood_claim(slots, mask, key);
+        if (slot == 0xFFFFFFFFu) gf->overflow = 1u; else atomicAdd(&slots[slot].count, 1u);
+        pt_slot27[w] = slot;
+    }
+}
+__global__ void neighbourhood_fill_kernel(const float4* __restrict__ pts, unsigned n, const CellSlot* __restrict__ slots,
+                                          const GridParams* __restrict__ gf, const unsigned* __restrict__ pt_slot27,
+                                          unsigned* __restrict__ cursor, float4* __restrict__ lists) {
+    if (!gf->enabled || gf->overflow) return;
+    for (size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x; w < (size_t)n * 27u; w += (size_t)gridDim.x * blockDim.x) {
+        const unsigned slot = pt_slot27[w];
+        const unsigned i = (unsigned)(w / 27u);
+        float4 p = pts[i]; p.w = __uint_as_float(i);
+        lists[slots[slot].start + atomicAdd(&cursor[slot], 1u)] = p;
+    }
+}
+// the source is binned by the cells the queries will probe: fine when that level is usable, else coarse
+__global__ void binning_params_kernel(GridParams* gp) {
+    if (threadIdx.x == 0) gp[2] = (gp[1].enabled && !gp[1].overflow) ? gp[1] : gp[0];
 }
 
 // Two-level nearest neighbour.  Dense targets put tens of points into a coarse cell (its edge is
 // the inlier threshold, ~10x the point spacing in configs[1]) although the true neighbour is almost
-// always within a fraction of it.  The fine grid is searched first; if it returns a match closer than
-// the fine reach, no point outside its 27 cells can be closer or tie (they are all farther than the
-// reach), so that match IS the global lexicographic (d2, index) minimum.  Otherwise the coarse search,
-// which is exact for everything within the threshold, runs from scratch for that query.
+// always within a fraction of it.  The fine level is searched first; if it returns a match closer than
+// the fine reach, no point outside the 27 fine cells around the query can be closer or tie (they are all
+// farther than the reach), so that match IS the global lexicographic (d2, index) minimum.  Otherwise the
+// coarse search, which is exact for everything within the threshold, runs from scratch for that query.
 // (A warp-pooled variant that deals the surviving neighbour visits out 32 at a time and merges through
 // shared-memory atomicMin keys was measured and was not faster: 93 vs 95 us at 300k x 100k, slower on
 // sparse targets; the per-thread form is kept.)
-__device__ __forceinline__ void grid_nearest2(float px, float py, float pz, const GridView& coarse, const GridView& fine,
-                                              bool fine_on, float accept2, float& best_d2, unsigned& best_idx) {
-    unsigned pos;
-    if (fine_on) {
-        grid_nearest(px, py, pz, fine, best_d2, best_idx, pos);
-        if (best_idx != B3D_NO_MATCH && best_d2 < accept2) return;
+// One probe: the neighbourhood list of p's fine cell (see neighbourhood_* kernels).  Returns false if the cell has none.
+__device__ __forceinline__ bool neighbourhood_nearest(float px, float py, float pz, const GridView& d, float& best_d2, unsigned& best_idx) {
+    best_d2 = FLT_MAX; best_idx = B3D_NO_MATCH;
+    const unsigned long long key = pack_cell(cell_coord(px, d.inv), cell_coord(py, d.inv), cell_coord(pz, d.inv));
+    unsigned slot = hash_cell(key) & d.mask;
+    unsigned start = 0, count = 0;
+    for (int probe = 0; probe < kNeighbourhoodProbes; ++probe) {
+        const CellSlot s = d.slots[slot];
+        if (s.key == key) { start = s.start; count = s.count; break; }
+        if (s.key == kEmptyKey) return false;
+        slot = (slot + 1u) & d.mask;
     }
+    auto consider = [&](const float4 q) {
+        const float e0 = px - q.x, e1 = py - q.y, e2 = pz - q.z;
+        const float d2 = e0 * e0 + (e1 * e1 + e2 * e2);            // (p - q).squaredNorm()
+        const unsigned idx = __float_as_uint(q.w);
+        if (d2 < best_d2 || (d2 == best_d2 && idx < best_idx)) { best_d2 = d2; best_idx = idx; }
+    };
+    unsigned k = 0;
+    for (; k + 4 <= count; k += 4) {
+        const float4 q0 = d.pts[start + k], q1 = d.pts[start + k + 1], q2 = d.pts[start + k + 2], q3 = d.pts[start + k + 3];
+        consider(q0); consider(q1); consider(q2); consider(q3);
+    }
+    for (; k < count; ++k) consider(d.pts[start + k]);
+    return count != 0u;
+}
+
+__device__ __forceinline__ void grid_nearest2(float px, float py, float pz, const GridView& coarse, const GridView& fine,
+                                              bool fine_on, bool complete, float accept2, float& best_d2, unsigned& best_idx) {
+    if (fine_on) {
+        const bool found = neighbourhood_nearest(px, py, pz, fine, best_d2, best_idx);
+        if (complete || (found && best_d2 < accept2)) return;
+    }
+    unsigned pos;
     grid_nearest(px, py, pz, coarse, best_d2, best_idx, pos);
 }
 
@@ -235,7 +315,7 @@ icp_accumulate_kernel(const float4* __restrict__ src, unsigned n_src, const Devi
         const GridView gfine = make_view(fslots, fpts, gp + 1);
         transform_point(R, t, src[i], x, y, z);
         unsigned idx;
-        grid_nearest2(x, y, z, g, gfine, gp[1].enabled != 0u, gp[1].accept2, d2, idx);
+        grid_nearest2(x, y, z, g, gfine, gp[1].enabled != 0u && gp[1].overflow == 0u, gp[1].complete != 0u, gp[1].accept2, d2, idx);
         pos = idx;                                                           // original target index
         n_corr = (idx != B3D_NO_MATCH && !(sqrtf(d2) > thr)) ? 1 : 0;       // registration.cpp:337-338 (d == thr is kept)
     }
@@ -402,7 +482,7 @@ icp_search_kernel(const float4* __restrict__ src, unsigned n_src, const DeviceSt
     const unsigned orig = BINNED ? __float_as_uint(s.w) : i;
     float x, y, z, d2; unsigned idx;
     transform_point(R, t, s, x, y, z);
-    grid_nearest2(x, y, z, g, gfine, gp[1].enabled != 0u, gp[1].accept2, d2, idx);
+    grid_nearest2(x, y, z, g, gfine, gp[1].enabled != 0u && gp[1].overflow == 0u, gp[1].complete != 0u, gp[1].accept2, d2, idx);
     const bool keep = idx != B3D_NO_MATCH && !(sqrtf(d2) > thr);            // registration.cpp:337-338
     rec[orig] = make_float4(x, y, z, d2);
     match[orig] = keep ? idx : B3D_NO_MATCH;
@@ -645,16 +725,16 @@ static int build_grid(b3d_ctx* c, float thr, GridParams** gp_out, unsigned* capa
     const unsigned n = (unsigned)c->n_tgt;
     const unsigned capacity = pow2_at_least(2 * (size_t)n);
     B3D_CUDA(c, c->grid_slots.ensure(sizeof(CellSlot) * capacity));
-    B3D_CUDA(c, c->grid_cursor.ensure(2 * sizeof(GridParams)));          // [0] coarse (cell = 1.02 thr), [1] fine
-    B3D_CUDA(c, c->fine_slots.ensure(sizeof(CellSlot) * capacity));
-    B3D_CUDA(c, c->fine_pts.ensure(sizeof(float4) * (n ? n : 1)));
+    B3D_CUDA(c, c->grid_cursor.ensure(3 * sizeof(GridParams)));          // [0] coarse (cell = 1.02 thr), [1] fine, [2] the one the source is binned by
+    B3D_CUDA(c, c->fine_slots.ensure(sizeof(CellSlot) * 16));
+    B3D_CUDA(c, c->fine_pts.ensure(sizeof(float4) * 16));
     B3D_CUDA(c, c->grid_pts.ensure(sizeof(float4) * (n ? n : 1)));
     B3D_CUDA(c, c->grid_nrm.ensure(sizeof(float4) * (n ? n : 1)));
     B3D_CUDA(c, c->pt_slot.ensure(sizeof(unsigned) * (n ? n : 1)));
     B3D_CUDA(c, c->pt_rank.ensure(sizeof(unsigned) * (n ? n : 1)));
     GridParams* gp = c->grid_cursor.as<GridParams>();
     CellSlot* slots = c->grid_slots.as<CellSlot>();
-    B3D_CUDA(c, cudaMemsetAsync(gp, 0, 2 * sizeof(GridParams), c->stream));
+    B3D_CUDA(c, cudaMemsetAsync(gp, 0, 3 * sizeof(GridParams), c->stream));
     if (n) { grid_bounds_kernel<<<grid_for(n, 256, 2), 256, 0, c->stream>>>(c->tgt4.as<float4>(), n, gp); B3D_LAUNCHED(c); }
     grid_init_kernel<<<grid_for(capacity, 256, 4), 256, 0, c->stream>>>(slots, capacity, gp, thr, n);
     B3D_LAUNCHED(c);
@@ -675,27 +755,46 @@ static int build_grid(b3d_ctx* c, float thr, GridParams** gp_out, unsigned* capa
                                                                         c->pt_slot.as<unsigned>(), c->pt_rank.as<unsigned>(),
                                                                         c->grid_pts.as<float4>(), c->grid_nrm.as<float4>(), nullptr);
         B3D_LAUNCHED(c);
-        // ---- second level: a finer grid for the common case of a dense target (see grid_nearest2) ----
+        // ---- second level: neighbourhood lists over a finer cell size (see neighbourhood_* kernels) ----
         GridParams* gf = gp + 1;
-        CellSlot* fslots = c->fine_slots.as<CellSlot>();
-        fine_params_kernel<<<1, 32, 0, c->stream>>>(gp, gf, capacity, n);
+        fine_params_kernel<<<1, 32, 0, c->stream>>>(gp, gf, 0u, n);
         B3D_LAUNCHED(c);
-        slots_clear_kernel<<<grid_for(capacity, 256, 4), 256, 0, c->stream>>>(fslots, capacity);
-        B3D_LAUNCHED(c);
-        grid_insert_kernel<<<grid_for(n, 256, 8), 256, 0, c->stream>>>(c->tgt4.as<float4>(), n, fslots, gf, capacity - 1u, nullptr,
-                                                                       c->pt_slot.as<unsigned>(), c->pt_rank.as<unsigned>(), nullptr);
-        B3D_LAUNCHED(c);
-        SlotCount fcnt{fslots}; SlotStart fst{fslots};
-        scan_tile_sums_kernel<<<tiles, kScanThreads, 0, c->stream>>>(fcnt, capacity, c->scan_tmp.as<unsigned>());
-        B3D_LAUNCHED(c);
-        scan_tile_offsets_kernel<<<1, kScanThreads, 0, c->stream>>>(c->scan_tmp.as<unsigned>(), tiles, (unsigned*)nullptr);
-        B3D_LAUNCHED(c);
-        scan_emit_kernel<<<tiles, kScanThreads, 0, c->stream>>>(fcnt, fst, capacity, c->scan_tmp.as<unsigned>());
-        B3D_LAUNCHED(c);
-        grid_scatter_kernel<<<grid_for(n, 256, 8), 256, 0, c->stream>>>(c->tgt4.as<float4>(), nullptr, n, fslots, c->pt_slot.as<unsigned>(),
-                                                                        c->pt_rank.as<unsigned>(), c->fine_pts.as<float4>(), nullptr, gf);
-        B3D_LAUNCHED(c);
+        // table size: in the sparse ("complete") case 27 * occupied coarse cells bounds the number of list cells exactly; in the
+        // dense case a surface needs ~1.3 n and a solid ~7 n cells — 8 n slots, and a fill-up only disables the level
+        GridParams h[2];
+        B3D_CUDA(c, cudaMemcpyAsync(h, gp, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+        B3D_CUDA(c, cudaStreamSynchronize(c->stream));
+        if (h[1].enabled) {
+            const size_t want = h[1].complete ? 2 * 27 * (size_t)h[0].occupied : 8 * (size_t)n;
+            const unsigned ncap = pow2_at_least(want);
+            B3D_CUDA(c, c->fine_slots.ensure(sizeof(CellSlot) * ncap));
+            B3D_CUDA(c, c->fine_pts.ensure(sizeof(float4) * 27 * (size_t)n));
+            B3D_CUDA(c, c->nbh_slot27.ensure(sizeof(unsigned) * 27 * (size_t)n));
+            B3D_CUDA(c, c->nbh_cursor.ensure(sizeof(unsigned) * ncap));
+            CellSlot* nslots = c->fine_slots.as<CellSlot>();
+            const unsigned nmask = ncap - 1u;
+            B3D_CUDA(c, cudaMemcpyAsync(&gf->mask, &nmask, sizeof(unsigned), cudaMemcpyHostToDevice, c->stream));
+            slots_clear_kernel<<<grid_for(ncap, 256, 4), 256, 0, c->stream>>>(nslots, ncap);
+            B3D_LAUNCHED(c);
+            B3D_CUDA(c, cudaMemsetAsync(c->nbh_cursor.p, 0, sizeof(unsigned) * ncap, c->stream));
+            neighbourhood_count_kernel<<<grid_for(27ll * n, 256, 16), 256, 0, c->stream>>>(c->tgt4.as<float4>(), n, nslots, gf, c->nbh_slot27.as<unsigned>());
+            B3D_LAUNCHED(c);
+            const unsigned ntiles = (unsigned)div_up(ncap, kScanTile);
+            B3D_CUDA(c, c->scan_tmp.ensure(sizeof(unsigned) * (ntiles + 1)));
+            SlotCount fcnt{nslots}; SlotStart fst{nslots};
+            scan_tile_sums_kernel<<<ntiles, kScanThreads, 0, c->stream>>>(fcnt, ncap, c->scan_tmp.as<unsigned>());
+            B3D_LAUNCHED(c);
+            scan_tile_offsets_kernel<<<1, kScanThreads, 0, c->stream>>>(c->scan_tmp.as<unsigned>(), ntiles, (unsigned*)nullptr);
+            B3D_LAUNCHED(c);
+            scan_emit_kernel<<<ntiles, kScanThreads, 0, c->stream>>>(fcnt, fst, ncap, c->scan_tmp.as<unsigned>());
+            B3D_LAUNCHED(c);
+            neighbourhood_fill_kernel<<<grid_for(27ll * n, 256, 16), 256, 0, c->stream>>>(c->tgt4.as<float4>(), n, nslots, gf, c->nbh_slot27.as<unsigned>(),
+                                                                                        c->nbh_cursor.as<unsigned>(), c->fine_pts.as<float4>());
+            B3D_LAUNCHED(c);
+        }
     }
+    binning_params_kernel<<<1, 32, 0, c->stream>>>(gp);
+    B3D_LAUNCHED(c);
     *gp_out = gp; *capacity_out = capacity;
     return B3D_OK;
 }
@@ -764,7 +863,7 @@ int icp_run_impl(b3d_ctx* c, const float* T0, float thr, int max_iter, int p2pla
     }
     if (binned) {                                            // below that the reorder costs more than it saves
         StageTimer timer(c, 6);
-        rc = bin_source_by_cell(c, gp, st->out18, &src);
+        rc = bin_source_by_cell(c, gp + 2, st->out18, &src);
         if (rc != B3D_OK) return rc;
     }
     const int blocks = div_up(n_src, kIcpThreads);           // one query per thread
