@@ -120,7 +120,8 @@ __global__ void fine_params_kernel(const GridParams* __restrict__ gc, GridParams
     gf->mask = capacity - 1u;
     gf->max_abs_bits = gc->max_abs_bits;
     gf->n_points = n;
-    gf->enabled = usable ? 1u : 0u;
+    gf->enabled = 0u;                                          // set once the lists exist (build_neighbourhood_lists)
+    gf->occupied = usable ? 1u : 0u;                           // "wanted": the level can be built for this target
     gf->complete = (usable && !finer) ? 1u : 0u;
     const float reach = gf->cell * 0.98f - gf->slack;          // every target closer than this lies in the 27 fine cells
     gf->accept2 = (finer && reach > 0.0f) ? __fmul_rd(reach, reach) * 0.999f : 0.0f;
@@ -755,47 +756,58 @@ static int build_grid(b3d_ctx* c, float thr, GridParams** gp_out, unsigned* capa
                                                                         c->pt_slot.as<unsigned>(), c->pt_rank.as<unsigned>(),
                                                                         c->grid_pts.as<float4>(), c->grid_nrm.as<float4>(), nullptr);
         B3D_LAUNCHED(c);
-        // ---- second level: neighbourhood lists over a finer cell size (see neighbourhood_* kernels) ----
-        GridParams* gf = gp + 1;
-        fine_params_kernel<<<1, 32, 0, c->stream>>>(gp, gf, 0u, n);
+        fine_params_kernel<<<1, 32, 0, c->stream>>>(gp, gp + 1, 0u, n);     // decides the second level's cell; lists are built lazily
         B3D_LAUNCHED(c);
-        // table size: in the sparse ("complete") case 27 * occupied coarse cells bounds the number of list cells exactly; in the
-        // dense case a surface needs ~1.3 n and a solid ~7 n cells — 8 n slots, and a fill-up only disables the level
-        GridParams h[2];
-        B3D_CUDA(c, cudaMemcpyAsync(h, gp, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
-        B3D_CUDA(c, cudaStreamSynchronize(c->stream));
-        if (h[1].enabled) {
-            const size_t want = h[1].complete ? 2 * 27 * (size_t)h[0].occupied : 8 * (size_t)n;
-            const unsigned ncap = pow2_at_least(want);
-            B3D_CUDA(c, c->fine_slots.ensure(sizeof(CellSlot) * ncap));
-            B3D_CUDA(c, c->fine_pts.ensure(sizeof(float4) * 27 * (size_t)n));
-            B3D_CUDA(c, c->nbh_slot27.ensure(sizeof(unsigned) * 27 * (size_t)n));
-            B3D_CUDA(c, c->nbh_cursor.ensure(sizeof(unsigned) * ncap));
-            CellSlot* nslots = c->fine_slots.as<CellSlot>();
-            const unsigned nmask = ncap - 1u;
-            B3D_CUDA(c, cudaMemcpyAsync(&gf->mask, &nmask, sizeof(unsigned), cudaMemcpyHostToDevice, c->stream));
-            slots_clear_kernel<<<grid_for(ncap, 256, 4), 256, 0, c->stream>>>(nslots, ncap);
-            B3D_LAUNCHED(c);
-            B3D_CUDA(c, cudaMemsetAsync(c->nbh_cursor.p, 0, sizeof(unsigned) * ncap, c->stream));
-            neighbourhood_count_kernel<<<grid_for(27ll * n, 256, 16), 256, 0, c->stream>>>(c->tgt4.as<float4>(), n, nslots, gf, c->nbh_slot27.as<unsigned>());
-            B3D_LAUNCHED(c);
-            const unsigned ntiles = (unsigned)div_up(ncap, kScanTile);
-            B3D_CUDA(c, c->scan_tmp.ensure(sizeof(unsigned) * (ntiles + 1)));
-            SlotCount fcnt{nslots}; SlotStart fst{nslots};
-            scan_tile_sums_kernel<<<ntiles, kScanThreads, 0, c->stream>>>(fcnt, ncap, c->scan_tmp.as<unsigned>());
-            B3D_LAUNCHED(c);
-            scan_tile_offsets_kernel<<<1, kScanThreads, 0, c->stream>>>(c->scan_tmp.as<unsigned>(), ntiles, (unsigned*)nullptr);
-            B3D_LAUNCHED(c);
-            scan_emit_kernel<<<ntiles, kScanThreads, 0, c->stream>>>(fcnt, fst, ncap, c->scan_tmp.as<unsigned>());
-            B3D_LAUNCHED(c);
-            neighbourhood_fill_kernel<<<grid_for(27ll * n, 256, 16), 256, 0, c->stream>>>(c->tgt4.as<float4>(), n, nslots, gf, c->nbh_slot27.as<unsigned>(),
-                                                                                        c->nbh_cursor.as<unsigned>(), c->fine_pts.as<float4>());
-            B3D_LAUNCHED(c);
-        }
     }
     binning_params_kernel<<<1, 32, 0, c->stream>>>(gp);
     B3D_LAUNCHED(c);
     *gp_out = gp; *capacity_out = capacity;
+    return B3D_OK;
+}
+
+// Second level, built only for calls that are still iterating after kListsAfter iterations: refinements that converge in
+// a handful of iterations never pay for it, long runs amortise it within a few iterations.
+constexpr int kListsAfter = 8;
+static int build_neighbourhood_lists(b3d_ctx* c, GridParams* gp, bool* built) {
+    *built = false;
+    const unsigned n = (unsigned)c->n_tgt;
+    GridParams* gf = gp + 1;
+    GridParams h[2];
+    B3D_CUDA(c, cudaMemcpyAsync(h, gp, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    B3D_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (!h[1].occupied || n == 0) return B3D_OK;
+    // table size: in the sparse ("complete") case 27 * occupied coarse cells bounds the number of list cells exactly; in the
+    // dense case a surface needs ~1.3 n and a solid ~7 n cells — 8 n slots, and a fill-up only disables the level
+    const size_t want = h[1].complete ? 2 * 27 * (size_t)h[0].occupied : 8 * (size_t)n;
+    const unsigned ncap = pow2_at_least(want);
+    B3D_CUDA(c, c->fine_slots.ensure(sizeof(CellSlot) * ncap));
+    B3D_CUDA(c, c->fine_pts.ensure(sizeof(float4) * 27 * (size_t)n));
+    B3D_CUDA(c, c->nbh_slot27.ensure(sizeof(unsigned) * 27 * (size_t)n));
+    B3D_CUDA(c, c->nbh_cursor.ensure(sizeof(unsigned) * ncap));
+    CellSlot* nslots = c->fine_slots.as<CellSlot>();
+    const unsigned nmask = ncap - 1u, one = 1u;
+    B3D_CUDA(c, cudaMemcpyAsync(&gf->mask, &nmask, sizeof(unsigned), cudaMemcpyHostToDevice, c->stream));
+    B3D_CUDA(c, cudaMemcpyAsync(&gf->enabled, &one, sizeof(unsigned), cudaMemcpyHostToDevice, c->stream));
+    slots_clear_kernel<<<grid_for(ncap, 256, 4), 256, 0, c->stream>>>(nslots, ncap);
+    B3D_LAUNCHED(c);
+    B3D_CUDA(c, cudaMemsetAsync(c->nbh_cursor.p, 0, sizeof(unsigned) * ncap, c->stream));
+    neighbourhood_count_kernel<<<grid_for(27ll * n, 256, 16), 256, 0, c->stream>>>(c->tgt4.as<float4>(), n, nslots, gf, c->nbh_slot27.as<unsigned>());
+    B3D_LAUNCHED(c);
+    const unsigned ntiles = (unsigned)div_up(ncap, kScanTile);
+    B3D_CUDA(c, c->scan_tmp.ensure(sizeof(unsigned) * (ntiles + 1)));
+    SlotCount fcnt{nslots}; SlotStart fst{nslots};
+    scan_tile_sums_kernel<<<ntiles, kScanThreads, 0, c->stream>>>(fcnt, ncap, c->scan_tmp.as<unsigned>());
+    B3D_LAUNCHED(c);
+    scan_tile_offsets_kernel<<<1, kScanThreads, 0, c->stream>>>(c->scan_tmp.as<unsigned>(), ntiles, (unsigned*)nullptr);
+    B3D_LAUNCHED(c);
+    scan_emit_kernel<<<ntiles, kScanThreads, 0, c->stream>>>(fcnt, fst, ncap, c->scan_tmp.as<unsigned>());
+    B3D_LAUNCHED(c);
+    neighbourhood_fill_kernel<<<grid_for(27ll * n, 256, 16), 256, 0, c->stream>>>(c->tgt4.as<float4>(), n, nslots, gf, c->nbh_slot27.as<unsigned>(),
+                                                                                c->nbh_cursor.as<unsigned>(), c->fine_pts.as<float4>());
+    B3D_LAUNCHED(c);
+    binning_params_kernel<<<1, 32, 0, c->stream>>>(gp);
+    B3D_LAUNCHED(c);
+    *built = true;
     return B3D_OK;
 }
 
@@ -907,10 +919,16 @@ int icp_run_impl(b3d_ctx* c, const float* T0, float thr, int max_iter, int p2pla
                 B3D_LAUNCHED(c);
             }
             // poll the device-side done flag now and then so converged runs stop launching
-            if ((iter & 15) == 15 && iter + 1 < max_iter) {
+            if (((iter & 15) == 15 || iter == kListsAfter - 1) && iter + 1 < max_iter) {
                 B3D_CUDA(c, cudaMemcpyAsync(&c->h_state->done, &st->done, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
                 B3D_CUDA(c, cudaStreamSynchronize(c->stream));
                 if (c->h_state->done) break;
+                if (iter == kListsAfter - 1) {                      // a long run: build the second level now and re-bin by its cells
+                    bool built = false;
+                    rc = build_neighbourhood_lists(c, gp, &built);
+                    if (rc != B3D_OK) return rc;
+                    if (built && binned) { rc = bin_source_by_cell(c, gp + 2, st->T, &src); if (rc != B3D_OK) return rc; }
+                }
             }
         }
     }

@@ -8,7 +8,7 @@ for name, kw, thr_scale in [("C2 300k x 100k thr 5mm", {}, 1.0), ("C2 thr 1mm", 
     ic = syn.icp_case(**kw)
     thr = ic.threshold * thr_scale
     ctx.set_clouds(ic.source, ic.target, ic.target_normals)
-    ctx.icp_run(ic.T_init, thr, 5, True, False)
+    ctx.icp_run(ic.T_init, thr, 12, True, False)      # long enough to build (and allocate) the lazily built second level
     for plane in (True, False):
         t0 = time.perf_counter()
         T, fit, rmse, it = ctx.icp_run(ic.T_init, thr, 50, plane, False)
