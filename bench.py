@@ -354,6 +354,28 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def pipeline_cpu_estimate(scene_raw, voxel, n_src, n_model, H, sample=3000):
+    """The CPU path's time for the same scene, from the oracle port on one host core: voxelDownsample in full (O(N)), normals and
+    FPFH on a `sample`-point subset scaled quadratically (both are O(N^2) scans, registration.cpp:63-102), matching and scoring
+    from the per-pair rates of the headline's cpu_baseline run."""
+    from oracle import oracle as O
+    t0 = time.perf_counter(); down = O.voxel_downsample(scene_raw, voxel); t_down = time.perf_counter() - t0
+    sub = np.ascontiguousarray(down[:sample])
+    t0 = time.perf_counter(); nrm = O.estimate_normals(sub, 30); t_n = time.perf_counter() - t0
+    t0 = time.perf_counter(); O.compute_fpfh(sub, nrm, voxel * 5.0); t_f = time.perf_counter() - t0
+    scale = (float(n_src) / float(sub.shape[0])) ** 2
+    rng = np.random.default_rng(0)
+    a = rng.random((256, 33), dtype=np.float32); b = rng.random((20000, 33), dtype=np.float32)
+    t0 = time.perf_counter(); O.match_features(a, b); t_m = (time.perf_counter() - t0) / (256 * 20000)
+    src = rng.random((20000, 3), dtype=np.float32); corr = np.arange(20000, dtype=np.uint32)
+    t0 = time.perf_counter(); O.ransac(src, src, corr, voxel, 512, 2.0); t_s = (time.perf_counter() - t0) / (512 * 20000)
+    parts = {"voxel_downsample_s": t_down, "normals_s": t_n * scale, "fpfh_s": t_f * scale,
+             "matching_s": t_m * float(n_src) * float(n_model), "ransac_scoring_s": t_s * float(H) * float(n_src)}
+    return {"seconds": float(sum(parts.values())), "cores": 1, "kind": "port",
+            "sample": f"voxelDownsample in full; estimateNormals / computeFPFH on {sub.shape[0]} points x ({n_src}/{sub.shape[0]})^2; matching and "
+                      "scoring from measured per-pair rates; ICP omitted", **{k: float(v) for k, v in parts.items()}}
+
+
 def batched_registration(b3d, bdist, syn, dev, rank, world, barrier, flush, n_instances=64, threads=8, reps=3):
     """configs[3]: 64 object instances, each ransacRegistration(H=100000, conf 0.999) + icpRefine(<=200 it), dealt
     round-robin to the ranks (instance i -> rank i mod N), each rank driving its share from a pool of `threads`
@@ -477,6 +499,7 @@ def whole_pipeline(b3d, syn, flush, n_raw=1_000_000, voxel=0.0037, H=100_000):
         names = ["match", "ransac_prepare", "score", "select_finish", "icp_grid", "icp_iterations", "icp_binning", "voxel_downsample",
                  "normals", "fpfh"]
         T = a["refined"][0]
+        res["cpu_port_estimate"] = pipeline_cpu_estimate(scene_raw, voxel, a["n_source_points"], n_model, H)
         res.update({"workload": f"raw {n_raw}-point scene -> {a['n_source_points']} points vs {n_model}-point model (voxel {voxel}); one "
                                 "b3d_register_scene call = voxelDownsample + estimateNormals(30) + computeFPFH(5*voxel) + ransacRegistration"
                                 f"(H={H}, conf 0.999) + icpRefine(0.4*voxel, <=200 it); real FPFH descriptors; pinned host buffer in, pose out",
