@@ -100,7 +100,8 @@ match_center_kernel(const float* __restrict__ tdesc, unsigned n, MatchAux* __res
 
 template <bool IS_B>
 __global__ void match_prep_kernel(const float* __restrict__ desc, unsigned n, unsigned n_padded,
-                                  __nv_bfloat16* __restrict__ tiles, float* __restrict__ norm2, MatchAux* __restrict__ aux) {
+                                  __nv_bfloat16* __restrict__ tiles, float* __restrict__ norm2, MatchAux* __restrict__ aux,
+                                  unsigned* __restrict__ tile_bmax_bits) {
     constexpr int ROWS = IS_B ? kTcN : kTcM;
     const unsigned r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_padded) return;
@@ -127,7 +128,7 @@ __global__ void match_prep_kernel(const float* __restrict__ desc, unsigned n, un
             float r2 = r1 - __bfloat162float(c1);
             row[99] = c0; row[100] = c1; row[101] = __float2bfloat16_rn(r2);
             float nb = (float)sqrt(s2) * 1.0000002f;
-            if (isfinite(nb)) atomicMax(&aux->max_bnorm_bits, __float_as_uint(nb));
+            if (isfinite(nb)) { atomicMax(&aux->max_bnorm_bits, __float_as_uint(nb)); atomicMax(&tile_bmax_bits[r / ROWS], __float_as_uint(nb)); }
         } else {
             row[99] = row[100] = row[101] = __float2bfloat16_rn(1.0f);
             norm2[r] = (float)s2;
@@ -233,7 +234,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 match_tc_kernel(const __nv_bfloat16* __restrict__ a_tiles, const __nv_bfloat16* __restrict__ b_tiles,
                 const float* __restrict__ sdesc, const float* __restrict__ tdesc, const float* __restrict__ a_norm2,
                 const MatchAux* __restrict__ aux, unsigned row0, unsigned row1, unsigned n_tgt,
-                unsigned rb_first, unsigned n_rb, unsigned n_nt, unsigned long long* __restrict__ best) {
+                unsigned rb_first, unsigned n_rb, unsigned n_nt, unsigned long long* __restrict__ best,
+                const unsigned* __restrict__ tile_bmax_bits) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const uint32_t a_smem = smem_u32(smem);
@@ -323,7 +325,7 @@ match_tc_kernel(const __nv_bfloat16* __restrict__ a_tiles, const __nv_bfloat16* 
         const float bmax = __uint_as_float(aux->max_bnorm_bits);
         uint32_t acc = 0, acc_phase = 0;
         unsigned cur_rb = 0xFFFFFFFFu, since_refresh = 0;
-        unsigned i = 0; bool row_live = false; float na = 0.0f, band = 0.0f, best_d = FLT_MAX, u = INFINITY;
+        unsigned i = 0; bool row_live = false; float na = 0.0f, ra = 0.0f, band = 0.0f, best_d = FLT_MAX, u = INFINITY;
         auto threshold = [&]() {
             float t = bad ? -INFINITY : 0.5f * ((na - best_d) - band) - 1e-30f;
             return (t == t) ? t : -INFINITY;               // NaN norm => re-score everything
@@ -349,11 +351,19 @@ match_tc_kernel(const __nv_bfloat16* __restrict__ a_tiles, const __nv_bfloat16* 
                 i = (rb_first + rb) * kTcM + quarter * 32 + lane;
                 row_live = (i >= row0 && i < row1);
                 na = 0.0f; band = 0.0f;
+                ra = 0.0f;
                 if (row_live) {
                     na = a_norm2[i];
-                    float s = sqrtf(na) * 1.0000002f + bmax;
+                    ra = sqrtf(na) * 1.0000002f;
+                    float s = ra + bmax;
                     band = kBandKappa * s * s;
                 }
+            }
+            {   // the band only has to cover THIS tile's targets: (|a'| + max over the tile of |b'|)^2 instead of the global maximum
+                const float tb = fminf(__uint_as_float(tile_bmax_bits[nt]), bmax);
+                const float s = ra + tb;
+                const float tile_band = kBandKappa * s * s;
+                if (tile_band != band) { band = tile_band; u = row_live ? threshold() : INFINITY; }
             }
             if (++since_refresh >= 4) {                    // other warps tighten the row's best too; a stale value is only looser
                 since_refresh = 0;
@@ -410,15 +420,17 @@ int match_features_tc_impl(b3d_ctx* c, size_t row0, size_t row1) {
     B3D_CUDA(c, c->tc_norm2.ensure(sizeof(float) * (size_t)n_rb_all * kTcM));
     B3D_CUDA(c, c->tc_best.ensure(sizeof(unsigned long long) * (size_t)n_src));
     B3D_CUDA(c, c->tc_aux.ensure(sizeof(MatchAux)));
+    B3D_CUDA(c, c->tc_aux.ensure(sizeof(MatchAux) + sizeof(unsigned) * n_nt));
     MatchAux* aux = c->tc_aux.as<MatchAux>();
-    B3D_CUDA(c, cudaMemsetAsync(aux, 0, sizeof(MatchAux), c->stream));
+    unsigned* tile_bmax = reinterpret_cast<unsigned*>(aux + 1);
+    B3D_CUDA(c, cudaMemsetAsync(aux, 0, sizeof(MatchAux) + sizeof(unsigned) * n_nt, c->stream));
     match_center_kernel<<<1, kDescDim * kCenterGroups, 0, c->stream>>>(c->tdesc_p, n_tgt, aux);
     B3D_LAUNCHED(c);
     match_prep_kernel<false><<<div_up(n_rb_all * kTcM, 128), 128, 0, c->stream>>>(c->sdesc_p, n_src, n_rb_all * kTcM, c->tc_a_tiles.as<__nv_bfloat16>(),
-                                                                                  c->tc_norm2.as<float>(), aux);
+                                                                                  c->tc_norm2.as<float>(), aux, nullptr);
     B3D_LAUNCHED(c);
     match_prep_kernel<true><<<div_up(n_nt * kTcN, 128), 128, 0, c->stream>>>(c->tdesc_p, n_tgt, n_nt * kTcN, c->tc_b_tiles.as<__nv_bfloat16>(),
-                                                                             nullptr, aux);
+                                                                             nullptr, aux, tile_bmax);
     B3D_LAUNCHED(c);
     match_seed_kernel<<<div_up((long long)(row1 - row0), 128), 128, 0, c->stream>>>(c->sdesc_p, c->tdesc_p, (unsigned)row0, (unsigned)row1, n_tgt,
                                                                                     c->tc_best.as<unsigned long long>());
@@ -435,7 +447,7 @@ int match_features_tc_impl(b3d_ctx* c, size_t row0, size_t row1) {
     match_tc_kernel<<<grid, kTcThreads, kTcSmemBytes, c->stream>>>(c->tc_a_tiles.as<__nv_bfloat16>(), c->tc_b_tiles.as<__nv_bfloat16>(),
                                                                    c->sdesc_p, c->tdesc_p, c->tc_norm2.as<float>(), aux,
                                                                    (unsigned)row0, (unsigned)row1, n_tgt, rb_first, n_rb, n_nt,
-                                                                   c->tc_best.as<unsigned long long>());
+                                                                   c->tc_best.as<unsigned long long>(), tile_bmax);
     B3D_LAUNCHED(c);
     match_finalize_kernel<<<div_up((long long)(row1 - row0), 256), 256, 0, c->stream>>>(c->tc_best.as<unsigned long long>(), (unsigned)row0, (unsigned)row1,
                                                                                        c->corr.as<uint32_t>());
