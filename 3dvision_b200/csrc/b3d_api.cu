@@ -124,7 +124,7 @@ void b3d_ctx_destroy(b3d_ctx* c) {
     DevBuf* bufs[] = {&c->stage_a, &c->stage_b, &c->stage_c, &c->src4, &c->tgt4, &c->nrm4, &c->sdesc, &c->tdesc, &c->corr, &c->raw,
                       &c->draws, &c->scan_tmp, &c->hyp, &c->counts, &c->pairs, &c->seqsum, &c->grid_slots, &c->grid_cursor,
                       &c->grid_pts, &c->grid_nrm, &c->pt_slot, &c->pt_rank, &c->partials, &c->nn_idx, &c->nn_d2, &c->state,
-                      &c->seq_rec, &c->seq_match, &c->seq_P, &c->seq_Q, &c->seq_N, &c->fine_slots, &c->fine_pts, &c->nbh_slot27, &c->nbh_cursor, &c->bail_list_a, &c->bail_list_b, &c->bail_state, &c->src_slots, &c->src_sorted, &c->src_slot, &c->src_rank,
+                      &c->seq_rec, &c->seq_match, &c->seq_P, &c->seq_Q, &c->seq_N, &c->fine_slots, &c->fine_pts, &c->nbh_slot27, &c->nbh_cursor, &c->icp_cache, &c->icp_cache_idx, &c->bail_list_a, &c->bail_list_b, &c->bail_state, &c->src_slots, &c->src_sorted, &c->src_slot, &c->src_rank,
                       &c->tc_a_tiles, &c->tc_b_tiles, &c->tc_norm2, &c->tc_best, &c->tc_aux};
     for (DevBuf* b : bufs) b->release();
     for (DevBuf& b : c->fbuf) b.release();

@@ -24,19 +24,20 @@ inline bool& alloc_stream_valid() { static thread_local bool v = false; return v
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
+    bool ordered_alloc = false;               // p came from cudaMallocAsync
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
     // Grow-only: steady-state calls with non-growing sizes never touch the allocator.
     cudaError_t ensure(size_t bytes) {
         if (bytes <= cap) return cudaSuccess;
         const bool ordered = alloc_stream_valid();
         if (p) {
-            cudaError_t e = ordered ? cudaFreeAsync(p, alloc_stream()) : cudaFree(p);
+            cudaError_t e = (ordered && ordered_alloc) ? cudaFreeAsync(p, alloc_stream()) : cudaFree(p);
             p = nullptr; cap = 0;
             if (e != cudaSuccess) return e;
         }
         size_t want = bytes + bytes / 4 + 256;
         cudaError_t e = ordered ? cudaMallocAsync(&p, want, alloc_stream()) : cudaMalloc(&p, want);
-        if (e == cudaSuccess) cap = want;
+        if (e == cudaSuccess) { cap = want; ordered_alloc = ordered; }
         return e;
     }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
@@ -108,6 +109,7 @@ struct b3d_ctx {
     b3d::DevBuf nn_idx, nn_d2;
     b3d::DevBuf fine_slots, fine_pts;                        // second ICP level: neighbourhood table + per-cell 27-cell point lists
     b3d::DevBuf nbh_slot27, nbh_cursor;
+    b3d::DevBuf icp_cache, icp_cache_idx;                    // per query slot: reference position + hold radius^2, and the match it certifies
     b3d::DevBuf seq_rec, seq_match, seq_P, seq_Q, seq_N;            // reference-order point-to-point: per-query records, compacted pairs
     int icp_mode = 0;                                        // 0: point-to-point adds in the reference's order; 1: fp64 tree sums everywhere; 2: reference order for plane too                        // second-level (finer) target grid
     b3d::DevBuf src_slots, src_sorted, src_slot, src_rank;   // source reordered by target cell (coherent warps)

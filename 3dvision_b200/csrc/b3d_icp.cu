@@ -124,7 +124,7 @@ __global__ void fine_params_kernel(const GridParams* __restrict__ gc, GridParams
     gf->occupied = usable ? 1u : 0u;                           // "wanted": the level can be built for this target
     gf->complete = (usable && !finer) ? 1u : 0u;
     const float reach = gf->cell * 0.98f - gf->slack;          // every target closer than this lies in the 27 fine cells
-    gf->accept2 = (finer && reach > 0.0f) ? __fmul_rd(reach, reach) * 0.999f : 0.0f;
+    gf->accept2 = (usable && reach > 0.0f) ? __fmul_rd(reach, reach) * 0.999f : 0.0f;
 }
 
 // Second level = per-cell NEIGHBOURHOOD LISTS.  Walking 27 hash cells per query is 27 dependent L2 round trips and
@@ -186,8 +186,14 @@ __global__ void binning_params_kernel(GridParams* gp) {
 // shared-memory atomicMin keys was measured and was not faster: 93 vs 95 us at 300k x 100k, slower on
 // sparse targets; the per-thread form is kept.)
 // One probe: the neighbourhood list of p's fine cell (see neighbourhood_* kernels).  Returns false if the cell has none.
-__device__ __forceinline__ bool neighbourhood_nearest(float px, float py, float pz, const GridView& d, float& best_d2, unsigned& best_idx) {
-    best_d2 = FLT_MAX; best_idx = B3D_NO_MATCH;
+// Keeps the kKeep lexicographically smallest (d2, index) candidates in order (bd[0], bi[0] is the match) and the smallest d2
+// among all the others (`next_d2`), which is what the re-use certificate of icp_match needs.
+constexpr int kKeep = 4;
+__device__ __forceinline__ bool neighbourhood_nearest(float px, float py, float pz, const GridView& d, float (&bd)[kKeep], unsigned (&bi)[kKeep],
+                                                      float& next_d2) {
+#pragma unroll
+    for (int k = 0; k < kKeep; ++k) { bd[k] = FLT_MAX; bi[k] = B3D_NO_MATCH; }
+    next_d2 = FLT_MAX;
     const unsigned long long key = pack_cell(cell_coord(px, d.inv), cell_coord(py, d.inv), cell_coord(pz, d.inv));
     unsigned slot = hash_cell(key) & d.mask;
     unsigned start = 0, count = 0;
@@ -199,9 +205,17 @@ __device__ __forceinline__ bool neighbourhood_nearest(float px, float py, float 
     }
     auto consider = [&](const float4 q) {
         const float e0 = px - q.x, e1 = py - q.y, e2 = pz - q.z;
-        const float d2 = e0 * e0 + (e1 * e1 + e2 * e2);            // (p - q).squaredNorm()
-        const unsigned idx = __float_as_uint(q.w);
-        if (d2 < best_d2 || (d2 == best_d2 && idx < best_idx)) { best_d2 = d2; best_idx = idx; }
+        float cd = e0 * e0 + (e1 * e1 + e2 * e2);                  // (p - q).squaredNorm()
+        unsigned ci = __float_as_uint(q.w);
+        if (!(cd < bd[kKeep - 1] || (cd == bd[kKeep - 1] && ci < bi[kKeep - 1]))) { next_d2 = fminf(next_d2, cd); return; }
+        next_d2 = fminf(next_d2, bd[kKeep - 1]);                   // the displaced last entry joins "the others"
+#pragma unroll
+        for (int k = 0; k < kKeep; ++k) {                          // insertion: bubble the new key down to its place
+            const bool before = cd < bd[k] || (cd == bd[k] && ci < bi[k]);
+            const float td = before ? bd[k] : cd; const unsigned ti = before ? bi[k] : ci;
+            bd[k] = before ? cd : bd[k]; bi[k] = before ? ci : bi[k];
+            cd = td; ci = ti;
+        }
     };
     unsigned k = 0;
     for (; k + 4 <= count; k += 4) {
@@ -212,14 +226,67 @@ __device__ __forceinline__ bool neighbourhood_nearest(float px, float py, float 
     return count != 0u;
 }
 
+// `hold2`: squared distance the query may move while its match provably stays among the kKeep candidates kept (0 = no
+// certificate).  The list holds every target within `reach`, so every target that is NOT kept is at least
+// min(next_d2, reach) away; by the triangle inequality the nearest target stays one of the kept ones while the query has
+// moved less than half the gap between that bound and the current best.
 __device__ __forceinline__ void grid_nearest2(float px, float py, float pz, const GridView& coarse, const GridView& fine,
-                                              bool fine_on, bool complete, float accept2, float& best_d2, unsigned& best_idx) {
+                                              bool fine_on, bool complete, float accept2, float& best_d2, unsigned& best_idx,
+                                              unsigned (&keep)[kKeep], float& hold2) {
+    hold2 = 0.0f;
+#pragma unroll
+    for (int k = 0; k < kKeep; ++k) keep[k] = B3D_NO_MATCH;
     if (fine_on) {
-        const bool found = neighbourhood_nearest(px, py, pz, fine, best_d2, best_idx);
-        if (complete || (found && best_d2 < accept2)) return;
+        float bd[kKeep], next_d2;
+        const bool found = neighbourhood_nearest(px, py, pz, fine, bd, keep, next_d2);
+        best_d2 = bd[0]; best_idx = keep[0];
+        if (complete || (found && best_d2 < accept2)) {
+            if (found) {
+                const float other = fminf(sqrtf(next_d2), sqrtf(accept2)) * 0.9999f;
+                const float gap = 0.5f * (other - sqrtf(best_d2)) - 2.0f * fine.slack;
+                hold2 = gap > 0.0f ? __fmul_rd(gap, gap) : 0.0f;
+            }
+            return;
+        }
     }
     unsigned pos;
     grid_nearest(px, py, pz, coarse, best_d2, best_idx, pos);
+}
+
+// One query of an iteration kernel.  `cache` keeps, per query slot, where the query stood when its match was last searched
+// and how far it may move before the search has to be repeated (see hold2), `cache_idx` the kKeep candidates that search kept:
+// once ICP has converged the pose changes by microns per iteration and almost every query only re-evaluates its kKeep
+// candidates exactly (kKeep gathers instead of a list scan).  The lexicographic (d2, index) minimum over them is what a fresh
+// search would return, so every sum downstream is unchanged.
+__device__ __forceinline__ void icp_match(float x, float y, float z, unsigned slot_i, const GridView& g, const GridView& gfine,
+                                          const GridParams* __restrict__ gp, const float4* __restrict__ tgt4,
+                                          float4* __restrict__ cache, uint4* __restrict__ cache_idx, float& d2, unsigned& idx) {
+    if (cache) {
+        const float4 c = cache[slot_i];
+        if (c.w > 0.0f) {
+            const float m0 = x - c.x, m1 = y - c.y, m2 = z - c.z;
+            if (m0 * m0 + (m1 * m1 + m2 * m2) < c.w) {
+                const uint4 k4 = cache_idx[slot_i];
+                const unsigned cand[kKeep] = {k4.x, k4.y, k4.z, k4.w};
+                d2 = FLT_MAX; idx = B3D_NO_MATCH;
+#pragma unroll
+                for (int k = 0; k < kKeep; ++k) {
+                    if (cand[k] == B3D_NO_MATCH) continue;
+                    const float4 q = tgt4[cand[k]];
+                    const float e0 = x - q.x, e1 = y - q.y, e2 = z - q.z;
+                    const float cd = e0 * e0 + (e1 * e1 + e2 * e2);            // (p - q).squaredNorm()
+                    if (cd < d2 || (cd == d2 && cand[k] < idx)) { d2 = cd; idx = cand[k]; }
+                }
+                return;
+            }
+        }
+    }
+    float hold2; unsigned keep[kKeep];
+    grid_nearest2(x, y, z, g, gfine, gp[1].enabled != 0u && gp[1].overflow == 0u, gp[1].complete != 0u, gp[1].accept2, d2, idx, keep, hold2);
+    if (cache) {
+        cache[slot_i] = make_float4(x, y, z, idx != B3D_NO_MATCH ? hold2 : 0.0f);
+        cache_idx[slot_i] = make_uint4(keep[0], keep[1], keep[2], keep[3]);
+    }
 }
 
 __device__ __forceinline__ void load_Rt(const float* __restrict__ T, float R[9], float t[3]) {
@@ -301,7 +368,8 @@ icp_accumulate_kernel(const float4* __restrict__ src, unsigned n_src, const Devi
                       const CellSlot* __restrict__ slots, const float4* __restrict__ gpts,
                       const CellSlot* __restrict__ fslots, const float4* __restrict__ fpts,
                       const float4* __restrict__ tgt4, const float4* __restrict__ nrm4,
-                      const GridParams* __restrict__ gp, double* __restrict__ partials) {
+                      const GridParams* __restrict__ gp, double* __restrict__ partials,
+                      float4* __restrict__ cache, uint4* __restrict__ cache_idx) {
     if (st->done) return;
     constexpr int NV = PLANE ? kAccPlane : kAccPoint;
     // ---- search phase (few live registers) ----
@@ -316,7 +384,7 @@ icp_accumulate_kernel(const float4* __restrict__ src, unsigned n_src, const Devi
         const GridView gfine = make_view(fslots, fpts, gp + 1);
         transform_point(R, t, src[i], x, y, z);
         unsigned idx;
-        grid_nearest2(x, y, z, g, gfine, gp[1].enabled != 0u && gp[1].overflow == 0u, gp[1].complete != 0u, gp[1].accept2, d2, idx);
+        icp_match(x, y, z, i, g, gfine, gp, tgt4, cache, cache_idx, d2, idx);
         pos = idx;                                                           // original target index
         n_corr = (idx != B3D_NO_MATCH && !(sqrtf(d2) > thr)) ? 1 : 0;       // registration.cpp:337-338 (d == thr is kept)
     }
@@ -471,7 +539,8 @@ __global__ void __launch_bounds__(kIcpThreads, 4)
 icp_search_kernel(const float4* __restrict__ src, unsigned n_src, const DeviceState* __restrict__ st, float thr,
                   const CellSlot* __restrict__ slots, const float4* __restrict__ gpts,
                   const CellSlot* __restrict__ fslots, const float4* __restrict__ fpts,
-                  const GridParams* __restrict__ gp, float4* __restrict__ rec, uint32_t* __restrict__ match) {
+                  const GridParams* __restrict__ gp, float4* __restrict__ rec, uint32_t* __restrict__ match,
+                  const float4* __restrict__ tgt4, float4* __restrict__ cache, uint4* __restrict__ cache_idx) {
     if (st->done) return;
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_src) return;
@@ -483,7 +552,7 @@ icp_search_kernel(const float4* __restrict__ src, unsigned n_src, const DeviceSt
     const unsigned orig = BINNED ? __float_as_uint(s.w) : i;
     float x, y, z, d2; unsigned idx;
     transform_point(R, t, s, x, y, z);
-    grid_nearest2(x, y, z, g, gfine, gp[1].enabled != 0u && gp[1].overflow == 0u, gp[1].complete != 0u, gp[1].accept2, d2, idx);
+    icp_match(x, y, z, i, g, gfine, gp, tgt4, cache, cache_idx, d2, idx);
     const bool keep = idx != B3D_NO_MATCH && !(sqrtf(d2) > thr);            // registration.cpp:337-338
     rec[orig] = make_float4(x, y, z, d2);
     match[orig] = keep ? idx : B3D_NO_MATCH;
@@ -880,6 +949,9 @@ int icp_run_impl(b3d_ctx* c, const float* T0, float thr, int max_iter, int p2pla
     }
     const int blocks = div_up(n_src, kIcpThreads);           // one query per thread
     B3D_CUDA(c, c->partials.ensure(sizeof(double) * kPartialStride * (size_t)blocks));
+    B3D_CUDA(c, c->icp_cache.ensure(sizeof(float4) * n_src)); B3D_CUDA(c, c->icp_cache_idx.ensure(sizeof(uint4) * n_src));
+    float4* cache = c->icp_cache.as<float4>(); uint4* cache_idx = c->icp_cache_idx.as<uint4>();
+    B3D_CUDA(c, cudaMemsetAsync(cache, 0, sizeof(float4) * n_src, c->stream));      // hold2 = 0: nothing to re-use yet
     {
         StageTimer timer(c, 5);
         const CellSlot* slots = c->grid_slots.as<CellSlot>();
@@ -887,16 +959,19 @@ int icp_run_impl(b3d_ctx* c, const float* T0, float thr, int max_iter, int p2pla
             if (plane && !replay) {
                 icp_accumulate_kernel<true><<<blocks, kIcpThreads, 0, c->stream>>>(src, n_src, st, thr, slots, c->grid_pts.as<float4>(),
                                                                                    c->fine_slots.as<CellSlot>(), c->fine_pts.as<float4>(),
-                                                                                   c->tgt4.as<float4>(), c->nrm4.as<float4>(), gp, c->partials.as<double>());
+                                                                                   c->tgt4.as<float4>(), c->nrm4.as<float4>(), gp, c->partials.as<double>(),
+                                                                                   cache, cache_idx);
                 B3D_LAUNCHED(c);
                 icp_update_kernel<true><<<1, kUpdateThreads, 0, c->stream>>>(c->partials.as<double>(), blocks, iter, (float)c->n_src, stop_on_conv, st);
                 B3D_LAUNCHED(c);
             } else if (replay) {
                 // reference-order sums: search -> ordered compaction -> sequential replay (see icp_seq_p2p_kernel)
                 if (binned) icp_search_kernel<true><<<blocks, kIcpThreads, 0, c->stream>>>(src, n_src, st, thr, slots, c->grid_pts.as<float4>(), c->fine_slots.as<CellSlot>(),
-                                                                                           c->fine_pts.as<float4>(), gp, c->seq_rec.as<float4>(), c->seq_match.as<uint32_t>());
+                                                                                           c->fine_pts.as<float4>(), gp, c->seq_rec.as<float4>(), c->seq_match.as<uint32_t>(),
+                                                                                           c->tgt4.as<float4>(), cache, cache_idx);
                 else        icp_search_kernel<false><<<blocks, kIcpThreads, 0, c->stream>>>(src, n_src, st, thr, slots, c->grid_pts.as<float4>(), c->fine_slots.as<CellSlot>(),
-                                                                                            c->fine_pts.as<float4>(), gp, c->seq_rec.as<float4>(), c->seq_match.as<uint32_t>());
+                                                                                            c->fine_pts.as<float4>(), gp, c->seq_rec.as<float4>(), c->seq_match.as<uint32_t>(),
+                                                                                           c->tgt4.as<float4>(), cache, cache_idx);
                 B3D_LAUNCHED(c);
                 MatchFlag flag{c->seq_match.as<uint32_t>()};
                 CompactPairs emit{c->seq_rec.as<float4>(), c->seq_match.as<uint32_t>(), c->tgt4.as<float4>(), c->seq_P.as<float4>(), c->seq_Q.as<float4>(),
@@ -913,7 +988,8 @@ int icp_run_impl(b3d_ctx* c, const float* T0, float thr, int max_iter, int p2pla
             } else {
                 icp_accumulate_kernel<false><<<blocks, kIcpThreads, 0, c->stream>>>(src, n_src, st, thr, slots, c->grid_pts.as<float4>(),
                                                                                     c->fine_slots.as<CellSlot>(), c->fine_pts.as<float4>(),
-                                                                                    c->tgt4.as<float4>(), c->nrm4.as<float4>(), gp, c->partials.as<double>());
+                                                                                    c->tgt4.as<float4>(), c->nrm4.as<float4>(), gp, c->partials.as<double>(),
+                                                                                   cache, cache_idx);
                 B3D_LAUNCHED(c);
                 icp_update_kernel<false><<<1, kUpdateThreads, 0, c->stream>>>(c->partials.as<double>(), blocks, iter, (float)c->n_src, stop_on_conv, st);
                 B3D_LAUNCHED(c);
@@ -927,7 +1003,10 @@ int icp_run_impl(b3d_ctx* c, const float* T0, float thr, int max_iter, int p2pla
                     bool built = false;
                     rc = build_neighbourhood_lists(c, gp, &built);
                     if (rc != B3D_OK) return rc;
-                    if (built && binned) { rc = bin_source_by_cell(c, gp + 2, st->T, &src); if (rc != B3D_OK) return rc; }
+                    if (built && binned) {
+                        rc = bin_source_by_cell(c, gp + 2, st->T, &src); if (rc != B3D_OK) return rc;
+                        B3D_CUDA(c, cudaMemsetAsync(cache, 0, sizeof(float4) * n_src, c->stream));      // query slots were re-ordered
+                    }
                 }
             }
         }
