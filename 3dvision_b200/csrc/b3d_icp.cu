@@ -995,11 +995,14 @@ int icp_run_impl(b3d_ctx* c, const float* T0, float thr, int max_iter, int p2pla
                 B3D_LAUNCHED(c);
             }
             // poll the device-side done flag now and then so converged runs stop launching
-            if (((iter & 15) == 15 || iter == kListsAfter - 1) && iter + 1 < max_iter) {
+            // a fixed-iteration request (no convergence break) of some length is known to be a long run: build the lists after the
+            // first two iterations (before that the queries are too far from the surface for the fine level to settle them)
+            const int lists_at = (!stop_on_conv && max_iter >= 2 * kListsAfter) ? 2 : kListsAfter;
+            if (((iter & 15) == 15 || iter == lists_at - 1) && iter + 1 < max_iter) {
                 B3D_CUDA(c, cudaMemcpyAsync(&c->h_state->done, &st->done, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
                 B3D_CUDA(c, cudaStreamSynchronize(c->stream));
                 if (c->h_state->done) break;
-                if (iter == kListsAfter - 1) {                      // a long run: build the second level now and re-bin by its cells
+                if (iter == lists_at - 1) {                         // a long run: build the second level now and re-bin by its cells
                     bool built = false;
                     rc = build_neighbourhood_lists(c, gp, &built);
                     if (rc != B3D_OK) return rc;
