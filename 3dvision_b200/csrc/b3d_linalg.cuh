@@ -207,58 +207,100 @@ B3D_HD float halving_sum(const float* c, int n) {
 }
 
 // A: symmetric 6x6, row-major a[r*6+c] (only the lower triangle is read). Solves A x = b.
+// Every array index below is a compile-time constant once the loops are unrolled (the pivot row is matched against
+// each candidate in a static loop instead of being used as an index), so on the device the whole factorisation lives
+// in registers; with run-time indices it sat in local memory and the one-thread solve cost ~13k cycles per ICP iteration.
 B3D_HD void ldlt6_solve(const float* A, const float* b, float* x) {
     float L[36];
+#pragma unroll
     for (int i = 0; i < 36; ++i) L[i] = A[i];
-    int perm[6];
+    int perm[6] = {0, 1, 2, 3, 4, 5};
     float tmp[6];
+    bool stop = false;
 #define LL(r, c) L[(r) * 6 + (c)]
+#define B3D_SWAP(a, b) { const float t_ = (a); (a) = (b); (b) = t_; }
+#pragma unroll
     for (int k = 0; k < 6; ++k) {
+        if (stop) continue;
         int piv = k; float pmax = fabsf(LL(k, k));
-        for (int i = k + 1; i < 6; ++i) { float v = fabsf(LL(i, i)); if (v > pmax) { pmax = v; piv = i; } }
+#pragma unroll
+        for (int i = k + 1; i < 6; ++i) { const float v = fabsf(LL(i, i)); if (v > pmax) { pmax = v; piv = i; } }
         perm[k] = piv;
-        if (piv != k) {
-            for (int j = 0; j < k; ++j) { float t = LL(k, j); LL(k, j) = LL(piv, j); LL(piv, j) = t; }
-            for (int i = piv + 1; i < 6; ++i) { float t = LL(i, k); LL(i, k) = LL(i, piv); LL(i, piv) = t; }
-            { float t = LL(k, k); LL(k, k) = LL(piv, piv); LL(piv, piv) = t; }
-            for (int i = k + 1; i < piv; ++i) { float t = LL(i, k); LL(i, k) = LL(piv, i); LL(piv, i) = t; }
+#pragma unroll
+        for (int p = k + 1; p < 6; ++p) {
+            if (piv != p) continue;
+#pragma unroll
+            for (int j = 0; j < k; ++j) B3D_SWAP(LL(k, j), LL(p, j));
+#pragma unroll
+            for (int i = p + 1; i < 6; ++i) B3D_SWAP(LL(i, k), LL(i, p));
+            B3D_SWAP(LL(k, k), LL(p, p));
+#pragma unroll
+            for (int i = k + 1; i < p; ++i) B3D_SWAP(LL(i, k), LL(p, i));
         }
         if (k > 0) {
+#pragma unroll
             for (int j = 0; j < k; ++j) tmp[j] = LL(j, j) * LL(k, j);
             float acc = LL(k, 0) * tmp[0];
+#pragma unroll
             for (int j = 1; j < k; ++j) acc = acc + LL(k, j) * tmp[j];
             LL(k, k) -= acc;
+#pragma unroll
             for (int i = k + 1; i < 6; ++i) {
                 float c = LL(i, 0) * tmp[0];
+#pragma unroll
                 for (int j = 1; j < k; ++j) c = c + LL(i, j) * tmp[j];
                 LL(i, k) -= c;
             }
         }
-        float d = LL(k, k);
-        bool ok = fabsf(d) > 0.0f;
-        if (k == 0 && !ok) { for (int j = 0; j < 6; ++j) perm[j] = j; break; }
-        if (ok) for (int i = k + 1; i < 6; ++i) LL(i, k) /= d;
+        const float d = LL(k, k);
+        const bool ok = fabsf(d) > 0.0f;
+        if (k == 0 && !ok) {
+#pragma unroll
+            for (int j = 0; j < 6; ++j) perm[j] = j;
+            stop = true;
+            continue;
+        }
+        if (ok) {
+#pragma unroll
+            for (int i = k + 1; i < 6; ++i) LL(i, k) /= d;
+        }
     }
     float y[6];
+#pragma unroll
     for (int i = 0; i < 6; ++i) y[i] = b[i];
-    for (int k = 0; k < 6; ++k) if (perm[k] != k) { float t = y[k]; y[k] = y[perm[k]]; y[perm[k]] = t; }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+#pragma unroll
+        for (int p = k + 1; p < 6; ++p) if (perm[k] == p) B3D_SWAP(y[k], y[p]);
+    }
+#pragma unroll
     for (int i = 1; i < 6; ++i) {
         float c[5];
+#pragma unroll
         for (int j = 0; j < i; ++j) c[j] = LL(i, j) * y[j];
         y[i] -= halving_sum(c, i);
     }
+#pragma unroll
     for (int i = 0; i < 6; ++i) y[i] = (fabsf(LL(i, i)) > FLT_MIN) ? (y[i] / LL(i, i)) : 0.0f;
+#pragma unroll
     for (int len = 1; len < 6; ++len) {
-        int row = 5 - len, first = row + 1;
+        const int row = 5 - len, first = row + 1;
         float c[5];
+#pragma unroll
         for (int j = 0; j < len; ++j) c[j] = LL(first + j, row) * y[first + j];
         float s;
         if (len >= 4) { s = (c[0] + c[2]) + (c[1] + c[3]); if (len == 5) s = s + c[4]; }
         else s = halving_sum(c, len);
         y[row] -= s;
     }
-    for (int k = 5; k >= 0; --k) if (perm[k] != k) { float t = y[k]; y[k] = y[perm[k]]; y[perm[k]] = t; }
+#pragma unroll
+    for (int k = 5; k >= 0; --k) {
+#pragma unroll
+        for (int p = k + 1; p < 6; ++p) if (perm[k] == p) B3D_SWAP(y[k], y[p]);
+    }
+#pragma unroll
     for (int i = 0; i < 6; ++i) x[i] = y[i];
+#undef B3D_SWAP
 #undef LL
 }
 
