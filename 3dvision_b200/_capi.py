@@ -31,7 +31,7 @@ SYMBOLS = [
     "b3d_correspondences_devptr", "b3d_set_score_mode", "b3d_ransac_prepare", "b3d_ransac_score", "b3d_ransac_reduce", "b3d_ransac_finish",
     "b3d_ransac_counts", "b3d_ransac_hypotheses", "b3d_set_icp_mode", "b3d_icp_run", "b3d_icp_nearest",
     "b3d_kernel_launches", "b3d_stage_ms", "b3d_measure_fp32_rate", "b3d_score_recounts",
-    "b3d_prepare_model", "b3d_register_scene", "b3d_depth_to_cloud", "b3d_register_depth", "b3d_voxel_downsample", "b3d_set_voxel_order_mode", "b3d_estimate_normals", "b3d_compute_fpfh",
+    "b3d_prepare_model", "b3d_register_scene", "b3d_register_scene_device", "b3d_depth_to_cloud", "b3d_register_depth", "b3d_voxel_downsample", "b3d_set_voxel_order_mode", "b3d_estimate_normals", "b3d_compute_fpfh",
 ]
 
 
@@ -113,6 +113,8 @@ def _declare(L):
                                      _vp, _vp, C.c_size_t, C.POINTER(C.c_size_t)]
     L.b3d_register_depth.argtypes = [_vp, _vp, C.c_int, C.c_int, _vp] + [C.c_float] * 6 + [C.c_float, C.c_int, C.c_float, C.c_int, C.c_float,
                                      C.c_float, C.c_int, C.c_int, C.POINTER(SceneResult)]
+    L.b3d_register_scene_device.argtypes = [_vp, _vp, C.c_size_t, C.c_float, C.c_int, C.c_float, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int,
+                                            C.POINTER(SceneResult)]
     L.b3d_prepare_model.argtypes = [_vp, _vp, C.c_size_t, C.c_float, C.c_int, C.c_float, C.POINTER(C.c_size_t)]
     L.b3d_register_scene.argtypes = [_vp, _vp, C.c_size_t, C.c_float, C.c_int, C.c_float, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int,
                                      C.POINTER(SceneResult)]
@@ -343,6 +345,20 @@ class Context:
         r = SceneResult()
         self._check(self._L.b3d_register_scene(self._h, _ptr(xyz), xyz.shape[0], voxel_size, int(normals_k), radius, int(ransac_max_iterations),
                                                confidence, thr, int(icp_max_iterations), int(bool(point_to_plane)), C.byref(r)))
+        self._n_src = r.n_source_points; self._H = int(ransac_max_iterations)
+        return {"coarse": (_T_from_colmajor(np.array(r.coarse_T, np.float32)), r.coarse_fitness, r.coarse_rmse, r.coarse_best_iteration),
+                "refined": (_T_from_colmajor(np.array(r.T, np.float32)), r.fitness, r.rmse, r.icp_iterations),
+                "n_source_points": int(r.n_source_points)}
+
+    def register_scene_device(self, scene_devptr: int, n: int, voxel_size, normals_k=30, fpfh_radius=None, ransac_max_iterations=100000,
+                              confidence=0.999, icp_threshold=None, icp_max_iterations=200, point_to_plane=True):
+        """register_scene for packed xyz floats already resident on this context's device (raw device address)."""
+        radius = voxel_size * 5.0 if fpfh_radius is None else fpfh_radius
+        thr = voxel_size * 0.4 if icp_threshold is None else icp_threshold
+        r = SceneResult()
+        self._check(self._L.b3d_register_scene_device(self._h, _ptr(int(scene_devptr)), int(n), voxel_size, int(normals_k), radius,
+                                                      int(ransac_max_iterations), confidence, thr, int(icp_max_iterations),
+                                                      int(bool(point_to_plane)), C.byref(r)))
         self._n_src = r.n_source_points; self._H = int(ransac_max_iterations)
         return {"coarse": (_T_from_colmajor(np.array(r.coarse_T, np.float32)), r.coarse_fitness, r.coarse_rmse, r.coarse_best_iteration),
                 "refined": (_T_from_colmajor(np.array(r.T, np.float32)), r.fitness, r.rmse, r.icp_iterations),

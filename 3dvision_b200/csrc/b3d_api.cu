@@ -248,6 +248,15 @@ int b3d_register_scene(b3d_ctx* c, const float* scene_xyz, size_t n, float voxel
                                icp_distance_threshold, icp_max_iterations, point_to_plane, out);
 }
 
+int b3d_register_scene_device(b3d_ctx* c, const float* scene_xyz_dev, size_t n, float voxel_size, int normals_k, float fpfh_radius,
+                              int ransac_max_iterations, float ransac_confidence, float icp_distance_threshold, int icp_max_iterations,
+                              int point_to_plane, b3d_scene_result* out) {
+    if (!c || !out || (n && !scene_xyz_dev)) return B3D_ERR_INVALID;
+    B3D_CUDA(c, enter(c));
+    return register_scene_device_impl(c, scene_xyz_dev, n, voxel_size, normals_k, fpfh_radius, ransac_max_iterations, ransac_confidence,
+                                      icp_distance_threshold, icp_max_iterations, point_to_plane, out);
+}
+
 int b3d_depth_to_cloud(b3d_ctx* c, const uint16_t* depth, int width, int height, const uint8_t* mask_or_null, float scale_to_meters,
                        float clipping_max, float fx, float fy, float cx, float cy, const uint8_t* bgr_or_null,
                        float* out_xyz, float* out_rgb_or_null, size_t capacity, size_t* out_n) {

@@ -187,6 +187,8 @@ int depth_to_cloud_impl(b3d_ctx* c, const uint16_t* depth, int w, int h, const u
 int register_depth_impl(b3d_ctx* c, const uint16_t* depth, int w, int h, const uint8_t* mask, float scale, float clip, float fx, float fy,
                         float cx, float cy, float voxel, int k, float radius, int ransac_iterations, float confidence, float icp_threshold,
                         int icp_iterations, int point_to_plane, b3d_scene_result* out);
+int register_scene_device_impl(b3d_ctx* c, const float* xyz_dev, size_t n, float voxel, int k, float radius, int ransac_iterations, float confidence,
+                               float icp_threshold, int icp_iterations, int point_to_plane, b3d_scene_result* out);
 int prepare_model_impl(b3d_ctx* c, const float* xyz, size_t n, float voxel, int k, float radius, size_t* out_n);
 int register_scene_impl(b3d_ctx* c, const float* xyz, size_t n, float voxel, int k, float radius, int ransac_iterations, float confidence,
                         float icp_threshold, int icp_iterations, int point_to_plane, b3d_scene_result* out);

@@ -953,6 +953,11 @@ int register_scene_impl(b3d_ctx* c, const float* xyz, size_t n, float voxel, int
     return register_resident(c, xyz, false, n, voxel, k, radius, ransac_iterations, confidence, icp_threshold, icp_iterations, point_to_plane, out);
 }
 
+int register_scene_device_impl(b3d_ctx* c, const float* xyz_dev, size_t n, float voxel, int k, float radius, int ransac_iterations, float confidence,
+                               float icp_threshold, int icp_iterations, int point_to_plane, b3d_scene_result* out) {
+    return register_resident(c, xyz_dev, true, n, voxel, k, radius, ransac_iterations, confidence, icp_threshold, icp_iterations, point_to_plane, out);
+}
+
 // depth image + mask of one instance -> pose: Pipeline::processInstance (pipeline.cpp:38-129) up to the refined transform
 int register_depth_impl(b3d_ctx* c, const uint16_t* depth, int w, int h, const uint8_t* mask, float scale, float clip, float fx, float fy,
                         float cx, float cy, float voxel, int k, float radius, int ransac_iterations, float confidence, float icp_threshold,

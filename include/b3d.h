@@ -189,6 +189,12 @@ int b3d_register_scene(b3d_ctx* ctx, const float* scene_xyz, size_t n, float vox
                        int ransac_max_iterations, float ransac_confidence, float icp_distance_threshold, int icp_max_iterations,
                        int point_to_plane, b3d_scene_result* out);
 
+/* b3d_register_scene for a cloud that already lives on this context's device (packed xyz floats, e.g. the output of a
+ * camera pipeline): no host hop at all.  The memory is only read, on the context's stream. */
+int b3d_register_scene_device(b3d_ctx* ctx, const float* scene_xyz_dev, size_t n, float voxel_size, int normals_k, float fpfh_radius,
+                              int ransac_max_iterations, float ransac_confidence, float icp_distance_threshold, int icp_max_iterations,
+                              int point_to_plane, b3d_scene_result* out);
+
 /* Depth image of one instance -> cloud: the CPU branch of Pipeline::processInstance, src/pipeline.cpp:38-84 (what
  * GPUDepth::preprocess + GPUPointCloud::generate, include/gpu_depth.hpp:9-22, do on the reference's GPU branch, but in
  * the CPU branch's raster order): z = depth / scale_to_meters; zero where mask <= 10 (mask_or_null == NULL: no

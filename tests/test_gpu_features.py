@@ -190,6 +190,11 @@ def test_register_scene_equals_the_five_separate_calls(b3d, ctx):
             assert np.array_equal(T0, coarse.transformation) and f0 == coarse.fitness and r0 == coarse.rmse
             assert np.array_equal(T1, fine.transformation) and f1 == fine.fitness and r1 == fine.rmse
         assert syn.rotation_error(T1, T_true) < 2e-3 and syn.translation_error(T1, T_true) < 1e-3      # and it registered
+        import torch                                            # device-resident input: same result, no host hop
+        d_scene = torch.from_numpy(scene_raw).cuda()
+        torch.cuda.synchronize()
+        dev = c2.register_scene_device(d_scene.data_ptr(), scene_raw.shape[0], voxel, ransac_max_iterations=20000, icp_max_iterations=50)
+        assert np.array_equal(dev["refined"][0], T1) and dev["refined"][1:3] == (f1, r1)
         empty = c2.register_scene(np.zeros((0, 3), np.float32), voxel)
         assert np.array_equal(empty["refined"][0], np.eye(4, dtype=np.float32)) and empty["refined"][1] == 0.0
     finally:
