@@ -496,11 +496,15 @@ __global__ void order_open_kernel(const unsigned* __restrict__ seq_prev, unsigne
     bucket_of[t] = b; elem[t] = r;
 }
 
-__global__ void order_key_kernel(const unsigned* __restrict__ open, const unsigned* __restrict__ bucket_of, unsigned n_now, int bits,
-                                 unsigned long long* __restrict__ keys) {
-    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_now) return;
-    keys[t] = ((unsigned long long)open[bucket_of[t]] << bits) | t;
+// Sort input in DESCENDING own time: a stable descending sort on the bucket's first-use time alone then leaves equal keys in
+// that order, i.e. the (first-use time, own time) descending order the container has — with half the key bits to sort.
+__global__ void order_key_kernel(const unsigned* __restrict__ open, const unsigned* __restrict__ bucket_of, const unsigned* __restrict__ elem,
+                                 unsigned n_now, unsigned* __restrict__ keys, unsigned* __restrict__ vals) {
+    const unsigned p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_now) return;
+    const unsigned t = n_now - 1u - p;
+    keys[p] = open[bucket_of[t]];
+    vals[p] = elem[t];
 }
 
 // perm[pos] = first-appearance rank of the voxel the reference emits at position pos
@@ -509,11 +513,11 @@ static int container_order_device(b3d_ctx* c, const int* key3_ordered, unsigned 
     rehash_schedule(m, steps);
     const unsigned max_buckets = steps.empty() ? 1u : steps.back().buckets;
     B3D_CUDA(c, c->fbuf[F_ORD_OPEN].ensure(sizeof(unsigned) * ((size_t)max_buckets + 2 * (size_t)m)));
-    B3D_CUDA(c, c->fbuf[F_ORD_KEYS].ensure(sizeof(unsigned long long) * 2 * (size_t)m));
+    B3D_CUDA(c, c->fbuf[F_ORD_KEYS].ensure(sizeof(unsigned) * 3 * (size_t)m));
     B3D_CUDA(c, c->fbuf[F_ORD_SEQ].ensure(sizeof(unsigned) * 2 * (size_t)m));
     unsigned* open = c->fbuf[F_ORD_OPEN].as<unsigned>();
     unsigned* bucket_of = open + max_buckets; unsigned* elem = bucket_of + m;
-    unsigned long long* keys_in = c->fbuf[F_ORD_KEYS].as<unsigned long long>(); unsigned long long* keys_out = keys_in + m;
+    unsigned* keys_in = c->fbuf[F_ORD_KEYS].as<unsigned>(); unsigned* keys_out = keys_in + m; unsigned* vals_in = keys_out + m;
     unsigned* seq[2] = {c->fbuf[F_ORD_SEQ].as<unsigned>(), c->fbuf[F_ORD_SEQ].as<unsigned>() + m};
     int cur = 0;
     unsigned n_prev = 0;
@@ -524,13 +528,13 @@ static int container_order_device(b3d_ctx* c, const int* key3_ordered, unsigned 
         B3D_CUDA(c, cudaMemsetAsync(open, 0xFF, sizeof(unsigned) * buckets, c->stream));
         order_open_kernel<<<div_up(n_now, 256), 256, 0, c->stream>>>(seq[cur], n_prev, n_now, key3_ordered, buckets, open, bucket_of, elem);
         B3D_LAUNCHED(c);
-        order_key_kernel<<<div_up(n_now, 256), 256, 0, c->stream>>>(open, bucket_of, n_now, bits, keys_in);
+        order_key_kernel<<<div_up(n_now, 256), 256, 0, c->stream>>>(open, bucket_of, elem, n_now, keys_in, vals_in);
         B3D_LAUNCHED(c);
         unsigned* dst = (p + 1 == steps.size()) ? perm : seq[cur ^ 1];
         size_t tmp_bytes = 0;
-        B3D_CUDA(c, cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp_bytes, keys_in, keys_out, elem, dst, (int)n_now, 0, 2 * bits, c->stream));
+        B3D_CUDA(c, cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp_bytes, keys_in, keys_out, vals_in, dst, (int)n_now, 0, bits, c->stream));
         B3D_CUDA(c, c->fbuf[F_CUB].ensure(tmp_bytes + 16));
-        B3D_CUDA(c, cub::DeviceRadixSort::SortPairsDescending(c->fbuf[F_CUB].p, tmp_bytes, keys_in, keys_out, elem, dst, (int)n_now, 0, 2 * bits, c->stream));
+        B3D_CUDA(c, cub::DeviceRadixSort::SortPairsDescending(c->fbuf[F_CUB].p, tmp_bytes, keys_in, keys_out, vals_in, dst, (int)n_now, 0, bits, c->stream));
         c->launches += 3;
         cur ^= 1;
         n_prev = n_now;
@@ -772,9 +776,10 @@ int voxel_downsample_dev(b3d_ctx* c, const float* d_xyz, unsigned n, const float
     voxel_mean_kernel<<<div_up(m, 128), 128, 0, c->stream>>>(d_xyz, d_col, n, keys_b, idx_b, c->fbuf[F_SEG].as<unsigned>(), flags + 1,
                                                              mean, mean_col, key3, first, vox);
     B3D_LAUNCHED(c);
-    B3D_CUDA(c, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, first, first_sorted, vox, order, (int)m, 0, 32, c->stream));
+    int first_bits = 1; while ((1ull << first_bits) < (unsigned long long)n) ++first_bits;     // first-appearance indices are < n
+    B3D_CUDA(c, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, first, first_sorted, vox, order, (int)m, 0, first_bits, c->stream));
     B3D_CUDA(c, c->fbuf[F_CUB].ensure(tmp_bytes + 16));
-    B3D_CUDA(c, cub::DeviceRadixSort::SortPairs(c->fbuf[F_CUB].p, tmp_bytes, first, first_sorted, vox, order, (int)m, 0, 32, c->stream));
+    B3D_CUDA(c, cub::DeviceRadixSort::SortPairs(c->fbuf[F_CUB].p, tmp_bytes, first, first_sorted, vox, order, (int)m, 0, first_bits, c->stream));
     c->launches += 4;
     gather_keys_kernel<<<div_up(m, 256), 256, 0, c->stream>>>(key3, order, m, key3_ordered);
     B3D_LAUNCHED(c);
