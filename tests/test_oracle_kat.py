@@ -242,3 +242,22 @@ def test_icp_converges_to_ground_truth(oracle):
     r = oracle.icp(c.source, c.target, c.target_normals, c.T_init, c.threshold, 40, True)
     assert syn.rotation_error(r.transformation, c.T_true) < 5e-3
     assert syn.translation_error(r.transformation, c.T_true) < 2e-3
+
+
+def test_depth_to_cloud_oracle_reproduces_the_demo_scene_and_known_pixels(oracle):
+    """pipeline.cpp:38-84 restated for any depth image: (a) on the procedural configs[0] images it must give exactly the
+    demo-scene builder's cloud; (b) hand-computed pixels: z = d/1000, x = (u-cx) z / fx, mask <= 10 and z > clip dropped."""
+    w, h = 1280, 720
+    u = np.arange(w)[None, :]; v = np.arange(h)[:, None]
+    depth = np.where((np.abs(u - w / 2.0) < 100) & (np.abs(v - h / 2.0) < 100), 800, 1000).astype(np.uint16)
+    mask = (((u >= w // 2 - 100) & (u <= w // 2 + 100) & (v >= h // 2 - 100) & (v <= h // 2 + 100)) * 255).astype(np.uint8)
+    xyz, _ = oracle.depth_to_cloud(depth, mask, 1000.0, 1.5, 900.0, 900.0, w / 2.0, h / 2.0)
+    assert np.array_equal(xyz.view(np.uint32), oracle.demo_scene_points().view(np.uint32))
+    d = np.array([[500, 0, 2000], [1500, 1501, 750]], np.uint16)
+    m = np.array([[255, 255, 255], [11, 255, 10]], np.uint8)
+    bgr = np.arange(18, dtype=np.uint8).reshape(2, 3, 3)
+    xyz, rgb = oracle.depth_to_cloud(d, m, 1000.0, 1.5, 2.0, 4.0, 1.0, 0.5, bgr=bgr)
+    # kept: (v=0,u=0) z=0.5; (v=1,u=0) z=1.5 (== clip is kept); dropped: zero depth, z=2.0 > clip, z=1.501 > clip, mask == 10
+    want = np.array([[(0 - 1.0) * 0.5 / 2.0, (0 - 0.5) * 0.5 / 4.0, 0.5], [(0 - 1.0) * 1.5 / 2.0, (1 - 0.5) * 1.5 / 4.0, 1.5]], np.float32)
+    assert np.array_equal(xyz, want)
+    assert np.allclose(rgb, np.array([[2, 1, 0], [11, 10, 9]], np.float32) / 255.0, atol=0, rtol=0)
