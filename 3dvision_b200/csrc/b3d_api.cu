@@ -302,7 +302,7 @@ int b3d_set_icp_mode(b3d_ctx* c, int mode) {
 }
 
 int b3d_set_score_mode(b3d_ctx* c, int mode) {
-    if (!c || mode < 0 || mode > 3) return B3D_ERR_INVALID;
+    if (!c || mode < 0 || mode > 4) return B3D_ERR_INVALID;
     c->score_mode = mode;
     return B3D_OK;
 }

@@ -102,6 +102,7 @@ struct b3d_ctx {
     int score_mode = 0;                      // 0 packed FMA screen, 1 un-fused everywhere, 2 scalar FMA screen, 3 bail-out (exact argmax)
     float ransac_thr = 0.f, ransac_cut = 0.f, confidence = 0.f;
     bool prepared = false, scored = false;
+    bool counts_pruned = false;              // the last scoring was a bail-out run: counts hold -4 marks
     int scored_lo = 0, scored_hi = 0;
 
     // ICP

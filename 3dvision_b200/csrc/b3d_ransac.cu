@@ -111,7 +111,7 @@ __global__ void hypothesis_kernel(const uint32_t* __restrict__ draws, const Devi
 
 __global__ void reset_counts_kernel(int* counts, int h0, int h1) {
     int h = h0 + blockIdx.x * blockDim.x + threadIdx.x;
-    if (h < h1 && counts[h] > 0) counts[h] = 0;
+    if (h < h1 && (counts[h] > 0 || counts[h] == -4)) counts[h] = 0;      // -4: dropped by an earlier bail-out run; -1 (degenerate) stays
 }
 
 // ---------------------------------------------------------------------------------
@@ -801,7 +801,7 @@ int ransac_prepare_impl(b3d_ctx* c, float voxel, int max_iterations, float confi
         if (attempt == 3) return fail(c, B3D_ERR_RNG_WINDOW, "ransac_prepare: RNG acceptance window exhausted");
         window *= 2;
     }
-    c->prepared = true;
+    c->prepared = true; c->counts_pruned = false;
     return B3D_OK;
 }
 
@@ -829,6 +829,7 @@ int ransac_generate_impl(b3d_ctx* c, int h0, int h1) {
 }
 
 static int ransac_score_bailout(b3d_ctx* c, int h0, int h1) {
+    c->counts_pruned = true;                      // ids it drops read -4 until the next full scoring or prepare
     const unsigned n = (unsigned)c->n_src, stride = c->pair_stride;
     const int nh = h1 - h0;
     B3D_CUDA(c, c->bail_list_a.ensure(sizeof(int) * (size_t)nh));
@@ -902,9 +903,14 @@ int ransac_score_impl(b3d_ctx* c, int h0, int h1) {
     const int nh = h1 - h0;
     // two hypotheses per thread (one packed FFMA2 lane pair) unless there are hardly any; the pair-range
     // split below supplies the parallelism when the id range is short (multi-GPU shards)
-    const int KH = (nh >= 2 * kScoreThreads) ? 2 : 1;
+    // ... and four (two packed pairs: two independent FFMA2 chains per thread, 123 registers, 16 warps/SM) when the range is long:
+    // the extra instruction-level parallelism keeps the FMA pipe busier than the occupancy it costs (63.7 -> 59.7 ms at 1M x 100k;
+    // six per thread, 166 registers, is back at 63.1 ms; capping registers for a third block spills: 68.6 ms)
+    const int KH = (nh >= 64 * kScoreThreads && c->score_mode != 4) ? 4 : (nh >= 2 * kScoreThreads) ? 2 : 1;
     if (c->score_mode == 3 && nh >= 8192 && n >= 16 * kPairTile) return ransac_score_bailout(c, h0, h1);
-    const int bx = div_up(nh, kScoreThreads * KH);
+    const bool packed_mode = c->score_mode == 0 || c->score_mode == 3 || c->score_mode == 4;
+    const int KHe = (KH == 4 && !packed_mode) ? 2 : KH;                     // the un-fused and scalar-screen kernels exist for 1 and 2 only
+    const int bx = div_up(nh, kScoreThreads * KHe);
     // Split the pair stream so that the grid is many waves deep: blocks are long-running and
     // compute-bound, so a shallow grid loses up to a full wave to the tail.
     int by = 1;
@@ -914,22 +920,24 @@ int ransac_score_impl(b3d_ctx* c, int h0, int h1) {
     unsigned per_y = (unsigned)div_up((long long)n, by);
     per_y = (unsigned)div_up(per_y, kPairTile) * kPairTile;
     by = div_up((long long)n, per_y);
-    if (by > 1) {
+    if (by > 1 || c->counts_pruned) {
         reset_counts_kernel<<<div_up(nh, 256), 256, 0, c->stream>>>(c->counts.as<int>(), h0, h1);
         B3D_LAUNCHED(c);
+        c->counts_pruned = false;
     }
     dim3 grid(bx, by);
     B3D_CUDA(c, cudaMemsetAsync(&c->state.as<DeviceState>()->score_recounts, 0, sizeof(unsigned long long), c->stream));
     const float4* pairs = c->pairs.as<float4>();
     const DeviceState* st = c->state.as<DeviceState>();
     if (c->score_mode == 1) {               // reference arithmetic for every pair (verification / comparison)
-        if (KH == 2) score_exact_kernel<2><<<grid, kScoreThreads, 0, c->stream>>>(c->hyp.as<float>(), c->H, h0, h1, pairs, n, c->pair_stride, per_y, c->ransac_cut, c->counts.as<int>());
+        if (KHe == 2) score_exact_kernel<2><<<grid, kScoreThreads, 0, c->stream>>>(c->hyp.as<float>(), c->H, h0, h1, pairs, n, c->pair_stride, per_y, c->ransac_cut, c->counts.as<int>());
         else         score_exact_kernel<1><<<grid, kScoreThreads, 0, c->stream>>>(c->hyp.as<float>(), c->H, h0, h1, pairs, n, c->pair_stride, per_y, c->ransac_cut, c->counts.as<int>());
-    } else if (c->score_mode == 0 || c->score_mode == 3) {   // packed FFMA2 screen (two hypotheses per instruction)
-        if (KH == 2) score_screen2_kernel<1><<<grid, kScoreThreads, 0, c->stream>>>(c->hyp.as<float>(), c->H, h0, h1, pairs, c->pair_stride, per_y, c->ransac_cut, c->ransac_thr, st, c->counts.as<int>(), ScoreSubset{nullptr, nullptr, nullptr, 0});
+    } else if (c->score_mode == 0 || c->score_mode == 3 || c->score_mode == 4) {   // packed FFMA2 screen (two hypotheses per instruction)
+        if (KH == 4) score_screen2_kernel<2><<<grid, kScoreThreads, 0, c->stream>>>(c->hyp.as<float>(), c->H, h0, h1, pairs, c->pair_stride, per_y, c->ransac_cut, c->ransac_thr, st, c->counts.as<int>(), ScoreSubset{nullptr, nullptr, nullptr, 0});
+        else if (KH == 2) score_screen2_kernel<1><<<grid, kScoreThreads, 0, c->stream>>>(c->hyp.as<float>(), c->H, h0, h1, pairs, c->pair_stride, per_y, c->ransac_cut, c->ransac_thr, st, c->counts.as<int>(), ScoreSubset{nullptr, nullptr, nullptr, 0});
         else         score_screen_kernel<1><<<grid, kScoreThreads, 0, c->stream>>>(c->hyp.as<float>(), c->H, h0, h1, pairs, c->pair_stride, per_y, c->ransac_cut, c->ransac_thr, st, c->counts.as<int>());
     } else {                                // scalar FMA screen
-        if (KH == 2) score_screen_kernel<2><<<grid, kScoreThreads, 0, c->stream>>>(c->hyp.as<float>(), c->H, h0, h1, pairs, c->pair_stride, per_y, c->ransac_cut, c->ransac_thr, st, c->counts.as<int>());
+        if (KHe == 2) score_screen_kernel<2><<<grid, kScoreThreads, 0, c->stream>>>(c->hyp.as<float>(), c->H, h0, h1, pairs, c->pair_stride, per_y, c->ransac_cut, c->ransac_thr, st, c->counts.as<int>());
         else         score_screen_kernel<1><<<grid, kScoreThreads, 0, c->stream>>>(c->hyp.as<float>(), c->H, h0, h1, pairs, c->pair_stride, per_y, c->ransac_cut, c->ransac_thr, st, c->counts.as<int>());
     }
     B3D_LAUNCHED(c);

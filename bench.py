@@ -290,11 +290,11 @@ def run_ours(args):
         # dram__bytes_read.sum + dram__bytes_write.sum of one full-size launch (ncu --set full, profiles/r1_final_ncu_score_match.csv:
         # 56.1 MB + 2.5 MB); the algorithmic bytes are 48 MB of hypotheses + 3.2 MB of pairs + 4 MB of counts = 55.2 MB
         "traffic": (58.6e6 if (h1 - h0) == N_HYP and N_SRC == 100_000 else None), "traffic_unit": "bytes/launch",
-        "kernel": "score_screen2_kernel", "kernel_ms": score_ms,
+        "kernel": "score_screen2_kernel<2>", "kernel_ms": score_ms,
         "note": ("SURVEY.md §8(d): RANSAC scoring is FP32 CUDA-core issue bound (not HBM, not tensor). achieved = 28 un-fused "
                  "fp32 ops (the reference's arithmetic) x hypotheses x correspondences per launch / CUDA-event kernel time; peak = "
                  "un-fused FMUL+FADD issue rate measured live on this GPU by b3d_measure_fp32_rate (MEASURED_PEAKS.json has no fp32 "
-                 "figure). frac > 1 is expected: the kernel screens with packed FFMA2 (15 fused ops instead of 27 un-fused per pair) "
+                 "figure). frac > 1 is expected: the kernel screens with packed FFMA2 (15 fused ops instead of 27 un-fused per pair, four hypotheses per thread) "
                  "and re-counts only pairs inside the proven error band with the reference arithmetic, so it retires the "
                  "reference's algorithmic work with fewer issued instructions; counts stay bit-identical (tests)."),
     }

@@ -127,7 +127,8 @@ int b3d_ransac_prepare(b3d_ctx* ctx, float voxel_size, int max_iterations, float
  * three give identical counts for every hypothesis.  3 = bail-out: hypotheses that provably cannot
  * reach the best full count found so far are dropped part-way (their count reads -4); the winner,
  * its transform, fitness and rmse are identical to modes 0-2, per-hypothesis counts are not all
- * available.  Not used by default. */
+ * available.  Not used by default.  4 = mode 0 restricted to two hypotheses per thread (mode 0 takes four per
+ * thread on long hypothesis ranges; kept for A/B timing). */
 int b3d_set_score_mode(b3d_ctx* ctx, int mode);
 /* src/registration.cpp:270-279 for hypothesis ids [h0,h1) (this rank's shard). */
 int b3d_ransac_score(b3d_ctx* ctx, int h0, int h1);
