@@ -845,7 +845,8 @@ static int ransac_score_bailout(b3d_ctx* c, int h0, int h1) {
     reset_counts_kernel<<<div_up(nh, 256), 256, 0, c->stream>>>(counts, h0, h1);
     B3D_LAUNCHED(c);
     // launch geometry: worst case (every id, every pair); blocks outside the device-side subset return at once
-    const int bx = div_up(nh, kScoreThreads * 2);
+    const bool wide = nh >= 64 * kScoreThreads;                              // four hypotheses per thread, as in ransac_score_impl
+    const int bx = div_up(nh, kScoreThreads * (wide ? 4 : 2));
     int by = 1;
     const int want_blocks = kNumSMs * 64;
     if (bx < want_blocks) by = min(div_up(want_blocks, bx), div_up((long long)n, kPairTile * 4));
@@ -854,8 +855,12 @@ static int ransac_score_bailout(b3d_ctx* c, int h0, int h1) {
     per_y = (unsigned)div_up(per_y, kPairTile) * kPairTile;
     by = div_up((long long)n, per_y);
     auto score = [&](int gx, const int* list, const int* n_list) -> int {
-        score_screen2_kernel<1><<<dim3(gx, by), kScoreThreads, 0, c->stream>>>(c->hyp.as<float>(), c->H, h0, h1, pairs, stride, per_y, c->ransac_cut,
-                                                                               c->ransac_thr, st, counts, ScoreSubset{list, n_list, bs->prange, 1});
+        if (wide && gx > 1)
+            score_screen2_kernel<2><<<dim3(gx, by), kScoreThreads, 0, c->stream>>>(c->hyp.as<float>(), c->H, h0, h1, pairs, stride, per_y, c->ransac_cut,
+                                                                                   c->ransac_thr, st, counts, ScoreSubset{list, n_list, bs->prange, 1});
+        else
+            score_screen2_kernel<1><<<dim3(gx, by), kScoreThreads, 0, c->stream>>>(c->hyp.as<float>(), c->H, h0, h1, pairs, stride, per_y, c->ransac_cut,
+                                                                                   c->ransac_thr, st, counts, ScoreSubset{list, n_list, bs->prange, 1});
         B3D_LAUNCHED(c);
         return B3D_OK;
     };
