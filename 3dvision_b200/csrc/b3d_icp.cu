@@ -848,7 +848,10 @@ static int build_neighbourhood_lists(b3d_ctx* c, GridParams* gp, bool* built) {
     // table size: in the sparse ("complete") case 27 * occupied coarse cells bounds the number of list cells exactly; in the
     // dense case a surface needs ~1.3 n and a solid ~7 n cells — 8 n slots, and a fill-up only disables the level
     const size_t want = h[1].complete ? 2 * 27 * (size_t)h[0].occupied : 8 * (size_t)n;
+    if (want > (1ull << 28)) return B3D_OK;                    // would not fit a 32-bit slot index comfortably: keep the walk
     const unsigned ncap = pow2_at_least(want);
+    // footprint: table + cursor per slot, list entry + slot id per (point, cell); a very large sparse target is not worth 4 GB
+    if ((size_t)ncap * (sizeof(CellSlot) + sizeof(unsigned)) + 27 * (size_t)n * (sizeof(float4) + sizeof(unsigned)) > (4ull << 30)) return B3D_OK;
     B3D_CUDA(c, c->fine_slots.ensure(sizeof(CellSlot) * ncap));
     B3D_CUDA(c, c->fine_pts.ensure(sizeof(float4) * 27 * (size_t)n));
     B3D_CUDA(c, c->nbh_slot27.ensure(sizeof(unsigned) * 27 * (size_t)n));
