@@ -287,9 +287,9 @@ def run_ours(args):
     peak = ctx.measure_fp32_rate() / 1e12
     roofline = {
         "bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-        # dram__bytes_read.sum + dram__bytes_write.sum of one full-size launch (ncu --set full, profiles/r1_final_ncu_score_match.csv:
-        # 56.1 MB + 2.5 MB); the algorithmic bytes are 48 MB of hypotheses + 3.2 MB of pairs + 4 MB of counts = 55.2 MB
-        "traffic": (58.6e6 if (h1 - h0) == N_HYP and N_SRC == 100_000 else None), "traffic_unit": "bytes/launch",
+        # dram__bytes_read.sum + dram__bytes_write.sum of one full-size launch (ncu --set full, profiles/r1_final_ncu_score_kp2.csv:
+        # 55.6 MB + 2.2 MB); the algorithmic bytes are 48 MB of hypotheses + 3.2 MB of pairs + 4 MB of counts = 55.2 MB
+        "traffic": (57.8e6 if (h1 - h0) == N_HYP and N_SRC == 100_000 else None), "traffic_unit": "bytes/launch",
         "kernel": "score_screen2_kernel<2>", "kernel_ms": score_ms,
         "note": ("SURVEY.md §8(d): RANSAC scoring is FP32 CUDA-core issue bound (not HBM, not tensor). achieved = 28 un-fused "
                  "fp32 ops (the reference's arithmetic) x hypotheses x correspondences per launch / CUDA-event kernel time; peak = "
