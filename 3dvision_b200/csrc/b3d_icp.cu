@@ -370,6 +370,9 @@ icp_accumulate_kernel(const float4* __restrict__ src, unsigned n_src, const Devi
                       const float4* __restrict__ tgt4, const float4* __restrict__ nrm4,
                       const GridParams* __restrict__ gp, double* __restrict__ partials,
                       float4* __restrict__ cache, uint4* __restrict__ cache_idx) {
+    // programmatic dependent launch: let the solve kernel behind us get resident now, and wait here for the one before us
+    cudaTriggerProgrammaticLaunchCompletion();
+    cudaGridDependencySynchronize();
     if (st->done) return;
     constexpr int NV = PLANE ? kAccPlane : kAccPoint;
     // ---- search phase (few live registers) ----
@@ -460,6 +463,8 @@ template <bool PLANE>
 __global__ void __launch_bounds__(kUpdateThreads)
 icp_update_kernel(const double* __restrict__ partials, int n_blocks, int iter, float n_src_f, int stop_on_convergence,
                   DeviceState* __restrict__ st) {
+    cudaTriggerProgrammaticLaunchCompletion();
+    cudaGridDependencySynchronize();
     if (st->done) return;
     // fixed-order (hence run-to-run deterministic) sum of the block partials: 8 strided groups, then 8 -> 1
     __shared__ double grp[kUpdateThreads / kPartialStride][kPartialStride];
@@ -834,6 +839,20 @@ static int build_grid(b3d_ctx* c, float thr, GridParams** gp_out, unsigned* capa
     return B3D_OK;
 }
 
+// Launch with programmatic stream serialization: the kernel may become resident while its predecessor is still running and
+// blocks in cudaGridDependencySynchronize() until that one has completed — the ~2-3 us of launch latency between the two
+// dependent kernels of an ICP iteration disappear behind the predecessor.
+template <class... KArgs, class... Args>
+static cudaError_t launch_dependent(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // Second level, built only for calls that are still iterating after kListsAfter iterations: refinements that converge in
 // a handful of iterations never pay for it, long runs amortise it within a few iterations.
 constexpr int kListsAfter = 8;
@@ -960,12 +979,13 @@ int icp_run_impl(b3d_ctx* c, const float* T0, float thr, int max_iter, int p2pla
         const CellSlot* slots = c->grid_slots.as<CellSlot>();
         for (int iter = 0; iter < max_iter; ++iter) {
             if (plane && !replay) {
-                icp_accumulate_kernel<true><<<blocks, kIcpThreads, 0, c->stream>>>(src, n_src, st, thr, slots, c->grid_pts.as<float4>(),
-                                                                                   c->fine_slots.as<CellSlot>(), c->fine_pts.as<float4>(),
-                                                                                   c->tgt4.as<float4>(), c->nrm4.as<float4>(), gp, c->partials.as<double>(),
-                                                                                   cache, cache_idx);
+                B3D_CUDA(c, launch_dependent(icp_accumulate_kernel<true>, dim3(blocks), dim3(kIcpThreads), c->stream, src, n_src, (const DeviceState*)st, thr,
+                                             slots, (const float4*)c->grid_pts.as<float4>(), (const CellSlot*)c->fine_slots.as<CellSlot>(),
+                                             (const float4*)c->fine_pts.as<float4>(), (const float4*)c->tgt4.as<float4>(), (const float4*)c->nrm4.as<float4>(),
+                                             (const GridParams*)gp, c->partials.as<double>(), cache, cache_idx));
                 B3D_LAUNCHED(c);
-                icp_update_kernel<true><<<1, kUpdateThreads, 0, c->stream>>>(c->partials.as<double>(), blocks, iter, (float)c->n_src, stop_on_conv, st);
+                B3D_CUDA(c, launch_dependent(icp_update_kernel<true>, dim3(1), dim3(kUpdateThreads), c->stream, (const double*)c->partials.as<double>(), blocks, iter,
+                                             (float)c->n_src, stop_on_conv, st));
                 B3D_LAUNCHED(c);
             } else if (replay) {
                 // reference-order sums: search -> ordered compaction -> sequential replay (see icp_seq_p2p_kernel)
