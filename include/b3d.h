@@ -235,7 +235,8 @@ int b3d_icp_nearest(b3d_ctx* ctx, const float T_colmajor[16], float distance_thr
 uint64_t b3d_kernel_launches(const b3d_ctx* ctx);
 /* Device time in ms of the last call of each stage, measured with CUDA events on the
  * context's stream: 0 match, 1 ransac_prepare, 2 ransac_score, 3 ransac_reduce+finish,
- * 4 icp grid build, 5 icp iterations, 6 icp source binning. Returns -1 for an unknown stage. */
+ * 4 icp grid build, 5 icp iterations (incl. the lazily built second level), 6 icp source binning, 7 voxel down-sampling,
+ * 8 normals, 9 FPFH. Returns -1 for an unknown stage or one that has not run. */
 float b3d_stage_ms(const b3d_ctx* ctx, int stage);
 
 /* Number of 32-pair groups the last b3d_ransac_score call had to re-count with the reference
