@@ -837,9 +837,9 @@ int voxel_downsample_impl(b3d_ctx* c, const float* xyz, size_t n_, const float* 
 // ---------------------------------------------------------------------------------
 struct DepthImage {
     const unsigned short* depth; const unsigned char* mask; const unsigned char* bgr;
-    int w; double inv_scale; float clip, fx, fy, cx, cy;
+    int w; float inv_scale; float clip, fx, fy, cx, cy;
     __device__ float z_at(unsigned px) const {
-        float z = (float)((double)depth[px] * inv_scale);                           // convertTo(CV_32FC1, 1.0 / scale_to_meters)
+        float z = (float)depth[px] * inv_scale;                                     // convertTo(CV_32FC1, 1.0 / scale): OpenCV scales 16u -> 32f in float
         if (mask && !(mask[px] > 10)) z = 0.0f;                                     // threshold(mask, 10) ; setTo(0, mask == 0)
         return z;
     }
@@ -877,7 +877,7 @@ static int depth_to_cloud_dev(b3d_ctx* c, const uint16_t* depth, int w, int h, c
         B3D_CUDA(c, cudaMemcpyAsync(c->fbuf[F_IMG_BGR].p, bgr, px * 3, cudaMemcpyHostToDevice, c->stream));
     }
     DepthImage im{c->fbuf[F_IMG_DEPTH].as<unsigned short>(), mask ? c->fbuf[F_IMG_MASK].as<unsigned char>() : nullptr,
-                  bgr ? c->fbuf[F_IMG_BGR].as<unsigned char>() : nullptr, w, 1.0 / (double)scale, clip, fx, fy, cx, cy};
+                  bgr ? c->fbuf[F_IMG_BGR].as<unsigned char>() : nullptr, w, (float)(1.0 / (double)scale), clip, fx, fy, cx, cy};
     PixelKept kept{im}; PixelEmit emit{im, c->fbuf[F_IMG_XYZ].as<float>(), bgr ? c->fbuf[F_IMG_RGB].as<float>() : nullptr};
     const unsigned tiles = (unsigned)div_up((long long)px, kScanTile);
     B3D_CUDA(c, c->scan_tmp.ensure(sizeof(unsigned) * (tiles + 2)));

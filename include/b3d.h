@@ -198,7 +198,7 @@ int b3d_register_scene_device(b3d_ctx* ctx, const float* scene_xyz_dev, size_t n
 
 /* Depth image of one instance -> cloud: the CPU branch of Pipeline::processInstance, src/pipeline.cpp:38-84 (what
  * GPUDepth::preprocess + GPUPointCloud::generate, include/gpu_depth.hpp:9-22, do on the reference's GPU branch, but in
- * the CPU branch's raster order): z = depth / scale_to_meters; zero where mask <= 10 (mask_or_null == NULL: no
+ * the CPU branch's raster order): z = float(depth) * float(1 / scale_to_meters) (OpenCV's 16u -> 32f convertTo); zero where mask <= 10 (mask_or_null == NULL: no
  * masking); keep 0 < z <= clipping_max; x = (u - cx) z / fx, y = (v - cy) z / fy; rgb = bgr reversed / 255.
  * Mask and colour image must have the depth image's size (the reference's nearest-neighbour mask resize is not done
  * here).  capacity / out_n as in b3d_voxel_downsample (width*height always suffices). */

@@ -163,8 +163,9 @@ size_t orc_demo_scene_points(int w, int h, float scale_to_meters, float clipping
             float z = floor_z;
             if (std::abs(u - cx) < 100 && std::abs(v - cy) < 100) z = box_z;
             unsigned short d_val = static_cast<unsigned short>(z * scale_to_meters);
-            // convertTo(CV_32F, 1/scale): saturate_cast<float>(d * alpha) computed in double
-            float fz = (float)((double)d_val * (1.0 / (double)scale_to_meters));
+            // convertTo(CV_32FC1, 1.0/scale): OpenCV's 16u -> 32f scaling works in float (cvtScale16u32f casts alpha to float and
+            // evaluates src*a + b per element, one rounding) — third-party behaviour, restated
+            float fz = (float)d_val * (float)(1.0 / (double)scale_to_meters);
             bool in_mask = (u >= mcx - 100 && u <= mcx + 100 && v >= mcy - 100 && v <= mcy + 100);  // cv::rectangle, inclusive
             if (!in_mask) fz = 0.0f;
             if (fz <= 0 || fz > clipping_max) continue;
@@ -177,7 +178,7 @@ size_t orc_demo_scene_points(int w, int h, float scale_to_meters, float clipping
 }
 
 // Mask + scale + deprojection of one instance, CPU branch of Pipeline::processInstance (pipeline.cpp:38-84), for any
-// depth image: convertTo(CV_32FC1, 1/scale); threshold(mask, 10, 255, BINARY) and setTo(0, mask_bool == 0) when a mask is
+// depth image: convertTo(CV_32FC1, 1/scale) [float arithmetic, as OpenCV's 16u->32f scaling]; threshold(mask, 10, 255, BINARY) and setTo(0, mask_bool == 0) when a mask is
 // given (apply_mask); skip z <= 0 or z > clipping_max; x = (u - cx) * z / fx; colours bgr -> rgb / 255.  Raster order.
 size_t orc_depth_to_cloud(const uint16_t* depth, int w, int h, const uint8_t* mask_or_null, float scale_to_meters, float clipping_max,
                           float fx, float fy, float cx, float cy, const uint8_t* bgr_or_null, float* xyz_out, float* rgb_out) {
@@ -185,7 +186,7 @@ size_t orc_depth_to_cloud(const uint16_t* depth, int w, int h, const uint8_t* ma
     for (int v = 0; v < h; ++v) {
         for (int u = 0; u < w; ++u) {
             const size_t px = (size_t)v * w + u;
-            float z = (float)((double)depth[px] * (1.0 / (double)scale_to_meters));
+            float z = (float)depth[px] * (float)(1.0 / (double)scale_to_meters);   // OpenCV cvtScale16u32f: float arithmetic, see above
             if (mask_or_null && !(mask_or_null[px] > 10)) z = 0.0f;
             if (z <= 0 || z > clipping_max) continue;
             xyz_out[3 * n] = (u - cx) * z / fx; xyz_out[3 * n + 1] = (v - cy) * z / fy; xyz_out[3 * n + 2] = z;

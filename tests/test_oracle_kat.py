@@ -246,7 +246,8 @@ def test_icp_converges_to_ground_truth(oracle):
 
 def test_depth_to_cloud_oracle_reproduces_the_demo_scene_and_known_pixels(oracle):
     """pipeline.cpp:38-84 restated for any depth image: (a) on the procedural configs[0] images it must give exactly the
-    demo-scene builder's cloud; (b) hand-computed pixels: z = d/1000, x = (u-cx) z / fx, mask <= 10 and z > clip dropped."""
+    demo-scene builder's cloud; (b) hand-computed pixels: z = float(d) * float(1/1000) (OpenCV scales 16u -> 32f in float),
+    x = (u-cx) z / fx, mask <= 10 and z > clip dropped — 1500 * float(0.001) rounds to 1.5000001 and is therefore clipped."""
     w, h = 1280, 720
     u = np.arange(w)[None, :]; v = np.arange(h)[:, None]
     depth = np.where((np.abs(u - w / 2.0) < 100) & (np.abs(v - h / 2.0) < 100), 800, 1000).astype(np.uint16)
@@ -257,7 +258,11 @@ def test_depth_to_cloud_oracle_reproduces_the_demo_scene_and_known_pixels(oracle
     m = np.array([[255, 255, 255], [11, 255, 10]], np.uint8)
     bgr = np.arange(18, dtype=np.uint8).reshape(2, 3, 3)
     xyz, rgb = oracle.depth_to_cloud(d, m, 1000.0, 1.5, 2.0, 4.0, 1.0, 0.5, bgr=bgr)
-    # kept: (v=0,u=0) z=0.5; (v=1,u=0) z=1.5 (== clip is kept); dropped: zero depth, z=2.0 > clip, z=1.501 > clip, mask == 10
-    want = np.array([[(0 - 1.0) * 0.5 / 2.0, (0 - 0.5) * 0.5 / 4.0, 0.5], [(0 - 1.0) * 1.5 / 2.0, (1 - 0.5) * 1.5 / 4.0, 1.5]], np.float32)
+    # kept: (v=0,u=0) z=0.5; dropped: zero depth, z=2.0 > clip, 1500 -> 1.5000001 > clip, 1501 > clip, mask == 10
+    a = np.float32(1.0 / 1000.0)
+    assert np.float32(1500) * a > np.float32(1.5) and np.float32(500) * a == np.float32(0.5)
+    want = np.array([[(0 - 1.0) * 0.5 / 2.0, (0 - 0.5) * 0.5 / 4.0, 0.5]], np.float32)
     assert np.array_equal(xyz, want)
-    assert np.allclose(rgb, np.array([[2, 1, 0], [11, 10, 9]], np.float32) / 255.0, atol=0, rtol=0)
+    assert np.allclose(rgb, np.array([[2, 1, 0]], np.float32) / 255.0, atol=0, rtol=0)
+    xyz2, _ = oracle.depth_to_cloud(d, m, 1000.0, 1.6, 2.0, 4.0, 1.0, 0.5)           # a looser clip keeps the 1.5000001 m and 1.501 m pixels
+    assert xyz2.shape[0] == 3 and xyz2[1, 2] == np.float32(1500) * a and xyz2[2, 2] == np.float32(1501) * a
