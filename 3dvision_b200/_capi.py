@@ -30,7 +30,7 @@ SYMBOLS = [
     "b3d_set_clouds", "b3d_set_features", "b3d_set_match_mode", "b3d_match_features", "b3d_get_correspondences", "b3d_get_correspondences_dev", "b3d_set_correspondences",
     "b3d_correspondences_devptr", "b3d_set_score_mode", "b3d_ransac_prepare", "b3d_ransac_score", "b3d_ransac_reduce", "b3d_ransac_finish",
     "b3d_ransac_counts", "b3d_ransac_hypotheses", "b3d_set_icp_mode", "b3d_icp_run", "b3d_icp_nearest",
-    "b3d_kernel_launches", "b3d_stage_ms", "b3d_measure_fp32_rate", "b3d_score_recounts",
+    "b3d_kernel_launches", "b3d_stage_ms", "b3d_measure_fp32_rate", "b3d_score_recounts", "b3d_icp_exact_sum_stats",
     "b3d_prepare_model", "b3d_register_scene", "b3d_register_scene_device", "b3d_depth_to_cloud", "b3d_register_depth", "b3d_voxel_downsample", "b3d_set_voxel_order_mode", "b3d_estimate_normals", "b3d_compute_fpfh",
 ]
 
@@ -107,6 +107,7 @@ def _declare(L):
     L.b3d_stage_ms.restype = C.c_float
     L.b3d_measure_fp32_rate.argtypes = [_vp, C.POINTER(C.c_double)]
     L.b3d_score_recounts.argtypes = [_vp, C.POINTER(C.c_uint64)]
+    L.b3d_icp_exact_sum_stats.argtypes = [_vp, C.POINTER(C.c_uint32)]
     L.b3d_voxel_downsample.argtypes = [_vp, _vp, C.c_size_t, _vp, C.c_float, _vp, _vp, C.c_size_t, C.POINTER(C.c_size_t)]
     L.b3d_set_voxel_order_mode.argtypes = [_vp, C.c_int]
     L.b3d_depth_to_cloud.argtypes = [_vp, _vp, C.c_int, C.c_int, _vp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _vp,
@@ -197,6 +198,12 @@ class Context:
         v = C.c_uint64()
         self._check(self._L.b3d_score_recounts(self._h, C.byref(v)))
         return int(v.value)
+
+    def icp_exact_sum_stats(self) -> np.ndarray:
+        """(32, 4) uint32: per running sum of the last ICP call: walk rounds, blocks added term by term, SM cycles / 16."""
+        out = np.zeros(128, np.uint32)
+        self._check(self._L.b3d_icp_exact_sum_stats(self._h, out.ctypes.data_as(C.POINTER(C.c_uint32))))
+        return out.reshape(32, 4)
 
     def measure_fp32_rate(self) -> float:
         """Sustained un-fused FMUL+FADD lane-ops/s on this device (scoring-kernel roofline)."""
@@ -316,7 +323,8 @@ class Context:
         return out
 
     def set_icp_mode(self, mode: int):
-        """0 (default): point-to-point sums in the reference's order (fp32, sequential); 1: fp64 tree sums."""
+        """0 (default): sums in the reference's order, exact and parallel; 1: fp64 tree sums (fast, opt-in);
+        3: reference order through one dependent add chain (cross-check)."""
         self._check(self._L.b3d_set_icp_mode(self._h, mode))
 
     def icp_run(self, T0, distance_threshold, max_iterations=200, point_to_plane=True, stop_on_convergence=True):

@@ -124,7 +124,7 @@ void b3d_ctx_destroy(b3d_ctx* c) {
     DevBuf* bufs[] = {&c->stage_a, &c->stage_b, &c->stage_c, &c->src4, &c->tgt4, &c->nrm4, &c->sdesc, &c->tdesc, &c->corr, &c->raw,
                       &c->draws, &c->scan_tmp, &c->hyp, &c->counts, &c->pairs, &c->seqsum, &c->grid_slots, &c->grid_cursor,
                       &c->grid_pts, &c->grid_nrm, &c->pt_slot, &c->pt_rank, &c->partials, &c->nn_idx, &c->nn_d2, &c->state,
-                      &c->seq_rec, &c->seq_match, &c->seq_P, &c->seq_Q, &c->seq_N, &c->fine_slots, &c->fine_pts, &c->nbh_slot27, &c->nbh_cursor, &c->icp_cache, &c->icp_cache_idx, &c->bail_list_a, &c->bail_list_b, &c->bail_state, &c->src_slots, &c->src_sorted, &c->src_slot, &c->src_rank,
+                      &c->seq_rec, &c->seq_match, &c->seq_P, &c->seq_Q, &c->seq_N, &c->ess_terms, &c->ess_bsum, &c->ess_guess, &c->ess_summ, &c->fine_slots, &c->fine_pts, &c->nbh_slot27, &c->nbh_cursor, &c->icp_cache, &c->icp_cache_idx, &c->bail_list_a, &c->bail_list_b, &c->bail_state, &c->src_slots, &c->src_sorted, &c->src_slot, &c->src_rank,
                       &c->tc_a_tiles, &c->tc_b_tiles, &c->tc_norm2, &c->tc_best, &c->tc_aux};
     for (DevBuf* b : bufs) b->release();
     for (DevBuf& b : c->fbuf) b.release();
@@ -182,7 +182,10 @@ int b3d_set_clouds(b3d_ctx* c, const float* src_xyz, size_t n_src, const float* 
     if ((n_src && !src_xyz) || (n_tgt && !tgt_xyz)) return fail(c, B3D_ERR_INVALID, "set_clouds: null cloud pointer");
     if (n_src >= 0xFFFFFFFFull || n_tgt >= 0xFFFFFFFFull) return fail(c, B3D_ERR_INVALID, "set_clouds: more than 2^32-2 points");
     B3D_CUDA(c, enter(c));
-    c->have_clouds = false; c->have_corr = false; c->prepared = false; c->scored = false; c->model_ready = false;
+    // new clouds invalidate everything sized by the old ones: descriptors too (they may be a caller's device pointer of the
+    // old n_src / n_tgt rows), so a stale set_features cannot be matched against the new clouds
+    c->have_clouds = false; c->have_feats = false; c->have_corr = false; c->prepared = false; c->scored = false; c->model_ready = false;
+    c->sdesc_p = nullptr; c->tdesc_p = nullptr;
     int rc = upload_cloud(c, src_xyz, n_src, on_device, c->stage_a, c->src4); if (rc) return rc;
     rc = upload_cloud(c, tgt_xyz, n_tgt, on_device, c->stage_b, c->tgt4); if (rc) return rc;
     c->has_normals = tgt_normals != nullptr;
@@ -198,6 +201,7 @@ int b3d_set_features(b3d_ctx* c, const float* src_desc, const float* tgt_desc, i
     if ((c->n_src && !src_desc) || (c->n_tgt && !tgt_desc)) return fail(c, B3D_ERR_INVALID, "set_features: null descriptor pointer");
     B3D_CUDA(c, enter(c));
     c->have_feats = false;
+    c->model_ready = false;                  // c->tdesc is about to be overwritten: the resident model's descriptors are gone
     if (on_device) { c->sdesc_p = src_desc; c->tdesc_p = tgt_desc; }
     else {
         const size_t sb = sizeof(float) * kDescDim * c->n_src, tb = sizeof(float) * kDescDim * c->n_tgt;
@@ -223,6 +227,14 @@ int b3d_score_recounts(b3d_ctx* c, uint64_t* out) {
     B3D_CUDA(c, cudaMemcpyAsync(&v, &c->state.as<DeviceState>()->score_recounts, sizeof(v), cudaMemcpyDeviceToHost, c->stream));
     B3D_CUDA(c, cudaStreamSynchronize(c->stream));
     *out = v;
+    return B3D_OK;
+}
+
+int b3d_icp_exact_sum_stats(b3d_ctx* c, uint32_t out[128]) {
+    if (!c || !out) return B3D_ERR_INVALID;
+    B3D_CUDA(c, enter(c));
+    B3D_CUDA(c, cudaMemcpyAsync(out, c->state.as<DeviceState>()->ess_stats, sizeof(uint32_t) * 128, cudaMemcpyDeviceToHost, c->stream));
+    B3D_CUDA(c, cudaStreamSynchronize(c->stream));
     return B3D_OK;
 }
 
@@ -296,7 +308,7 @@ int b3d_compute_fpfh(b3d_ctx* c, const float* xyz, const float* normals, size_t 
 }
 
 int b3d_set_icp_mode(b3d_ctx* c, int mode) {
-    if (!c || mode < 0 || mode > 2) return B3D_ERR_INVALID;
+    if (!c || mode < 0 || mode > 3) return B3D_ERR_INVALID;
     c->icp_mode = mode;
     return B3D_OK;
 }

@@ -61,6 +61,10 @@ struct DeviceState {
     int done;                         // 1 once converged / broke out
     int n_corr_last;
     unsigned int seq_count;           // matched pairs of the current reference-order ICP iteration
+    unsigned int ess_arrive;          // CTAs of the current exact-sum chain launch that have stored their sum
+    float ess_sums[32];               // the exact sequential sums of the current iteration (b3d_ess.cuh)
+    float ess_means[8];               // point-to-point: src_mean(3), tgt_mean(3) between the two passes
+    unsigned int ess_stats[32][4];    // per sum, accumulated over the call: walk rounds, blocks added term by term, SM cycles / 16 (diagnostic)
     float out18[20];                  // RANSAC result: T(16), fitness, rmse, best id (as int bits), unused
 };
 
@@ -111,8 +115,9 @@ struct b3d_ctx {
     b3d::DevBuf fine_slots, fine_pts;                        // second ICP level: neighbourhood table + per-cell 27-cell point lists
     b3d::DevBuf nbh_slot27, nbh_cursor;
     b3d::DevBuf icp_cache, icp_cache_idx;                    // per query slot: reference position + hold radius^2, and the match it certifies
-    b3d::DevBuf seq_rec, seq_match, seq_P, seq_Q, seq_N;            // reference-order point-to-point: per-query records, compacted pairs
-    int icp_mode = 0;                                        // 0: point-to-point adds in the reference's order; 1: fp64 tree sums everywhere; 2: reference order for plane too                        // second-level (finer) target grid
+    b3d::DevBuf seq_rec, seq_match, seq_P, seq_Q, seq_N;            // reference-order sums: per-query records (legacy chain: compacted pairs)
+    b3d::DevBuf ess_terms, ess_bsum, ess_guess, ess_summ;           // exact sequential sums (b3d_ess.cuh): terms, fp64 block sums, guesses, summaries
+    int icp_mode = 0;                                        // 0 / 2: sums in the reference's order (exact, parallel); 1: fp64 tree sums; 3: legacy one-chain replay
     b3d::DevBuf src_slots, src_sorted, src_slot, src_rank;   // source reordered by target cell (coherent warps)
 
     // feature stages (b3d_features.cu): scratch pool, slots named there

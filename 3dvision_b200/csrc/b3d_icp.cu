@@ -27,6 +27,7 @@
 #include "b3d_linalg.cuh"
 #include "b3d_scan.cuh"
 #include "b3d_grid.cuh"
+#include "b3d_ess.cuh"
 #include <float.h>
 #include <math.h>
 
@@ -541,7 +542,7 @@ icp_update_kernel(const double* __restrict__ partials, int n_blocks, int iter, f
 // ---------------------------------------------------------------------------------
 template <bool BINNED>
 __global__ void __launch_bounds__(kIcpThreads, 4)
-icp_search_kernel(const float4* __restrict__ src, unsigned n_src, const DeviceState* __restrict__ st, float thr,
+icp_search_kernel(const float4* __restrict__ src, unsigned n_src, DeviceState* __restrict__ st, float thr,
                   const CellSlot* __restrict__ slots, const float4* __restrict__ gpts,
                   const CellSlot* __restrict__ fslots, const float4* __restrict__ fpts,
                   const GridParams* __restrict__ gp, float4* __restrict__ rec, uint32_t* __restrict__ match,
@@ -549,6 +550,7 @@ icp_search_kernel(const float4* __restrict__ src, unsigned n_src, const DeviceSt
     if (st->done) return;
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_src) return;
+    if (i == 0) st->seq_count = 0u;                                         // counted again by this iteration's terms pass
     float R[9], t[3];
     load_Rt(st->T, R, t);
     const GridView g = make_view(slots, gpts, gp);
@@ -784,10 +786,139 @@ icp_seq_plane_kernel(const float4* __restrict__ P, const float4* __restrict__ Q,
     if (stop_on_convergence && iter > 0 && fabsf(prev_rmse - rmse) < 1e-6f) st->done = 1;
 }
 
+// ---------------------------------------------------------------------------------
+// Reference-order iteration, parallel (default): the sums of registration.cpp:341-358, 374-386 bit for bit without the
+// dependent add chain, see b3d_ess.cuh.  The search kernel leaves (p, d2) and the match of every query at its ORIGINAL
+// index; a terms pass forms each record's products exactly as the reference forms them (+0 for queries the reference
+// skips, which leaves an fp32 running sum untouched, so the records need no compaction); fp64 block sums -> guesses ->
+// integer block summaries; then one CTA per sum walks its summaries and the last CTA to arrive solves and updates T.
+// ---------------------------------------------------------------------------------
+struct PlaneTerms {                                   // ATA upper triangle (21), ATb (6), total_error
+    const float4* rec; const uint32_t* match; const float4* tgt4; const float4* nrm4;
+    __device__ __forceinline__ bool operator()(unsigned k, float (&t)[kAccPlane]) const {
+        const uint32_t j = match[k];
+        if (j == B3D_NO_MATCH) {
+#pragma unroll
+            for (int v = 0; v < kAccPlane; ++v) t[v] = 0.0f;
+            return false;
+        }
+        const float4 p = rec[k], q = tgt4[j], n = nrm4[j];
+        float J[6];
+        J[0] = p.y * n.z - p.z * n.y; J[1] = p.z * n.x - p.x * n.z; J[2] = p.x * n.y - p.y * n.x;      // p.cross(n), registration.cpp:346
+        J[3] = n.x; J[4] = n.y; J[5] = n.z;
+        const float a0 = (p.x - q.x) * n.x, a1 = (p.y - q.y) * n.y, a2 = (p.z - q.z) * n.z;
+        const float r = a0 + (a1 + a2);                                                                   // (p - q).dot(n)
+        int c = 0;
+#pragma unroll
+        for (int a = 0; a < 6; ++a)
+#pragma unroll
+            for (int b = a; b < 6; ++b) t[c++] = J[a] * J[b];
+#pragma unroll
+        for (int a = 0; a < 6; ++a) t[21 + a] = J[a] * r;
+        t[27] = p.w;
+        return true;
+    }
+};
+constexpr int kAccPoint0 = 7, kAccPoint1 = 9;
+struct PointTerms0 {                                  // src_mean sums (3), tgt_mean sums (3), total_error
+    const float4* rec; const uint32_t* match; const float4* tgt4;
+    __device__ __forceinline__ bool operator()(unsigned k, float (&t)[kAccPoint0]) const {
+        const uint32_t j = match[k];
+        if (j == B3D_NO_MATCH) {
+#pragma unroll
+            for (int v = 0; v < kAccPoint0; ++v) t[v] = 0.0f;
+            return false;
+        }
+        const float4 p = rec[k], q = tgt4[j];
+        t[0] = p.x; t[1] = p.y; t[2] = p.z; t[3] = q.x; t[4] = q.y; t[5] = q.z; t[6] = p.w;
+        return true;
+    }
+};
+struct PointTerms1 {                                  // H(r, c) += (p_r - src_mean_r) * (q_c - tgt_mean_c), registration.cpp:384-386
+    const float4* rec; const uint32_t* match; const float4* tgt4; const DeviceState* st;
+    __device__ __forceinline__ bool operator()(unsigned k, float (&t)[kAccPoint1]) const {
+        const uint32_t j = match[k];
+        if (j == B3D_NO_MATCH) {
+#pragma unroll
+            for (int v = 0; v < kAccPoint1; ++v) t[v] = 0.0f;
+            return false;
+        }
+        const float4 p = rec[k], q = tgt4[j];
+        const float pc[3] = {p.x - st->ess_means[0], p.y - st->ess_means[1], p.z - st->ess_means[2]};
+        const float qc[3] = {q.x - st->ess_means[3], q.y - st->ess_means[4], q.z - st->ess_means[5]};
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int b = 0; b < 3; ++b) t[a * 3 + b] = pc[a] * qc[b];
+        return true;
+    }
+};
+
+__device__ __forceinline__ void icp_commit(DeviceState* st, const float (&delta)[16], float total_error, int n, int iter, float n_src_f, int stop_on_convergence) {
+    float Tn[16];
+    mat4_mul(delta, st->T, Tn);                              // T = delta * T
+    const float prev_rmse = st->res_rmse;
+    const float rmse = sqrtf(total_error / (float)n);
+    for (int i = 0; i < 16; ++i) { st->T[i] = Tn[i]; st->res_T[i] = Tn[i]; }
+    st->res_rmse = rmse;
+    st->res_fitness = (float)n / n_src_f;
+    st->iterations = iter + 1;
+    if (stop_on_convergence && iter > 0 && fabsf(prev_rmse - rmse) < 1e-6f) st->done = 1;    // registration.cpp:406
+}
+
+// PHASE 0: point-to-plane sums -> solve.  1: point-to-point first pass -> means.  2: point-to-point second pass -> solve.
+template <int NV, int PHASE>
+__global__ void __launch_bounds__(ess::kChainThreads)
+icp_ess_chain_kernel(const float* __restrict__ terms, size_t stride, const ess::BlockSummary* __restrict__ summ, unsigned nb_stride, unsigned n,
+                     int iter, float n_src_f, int stop_on_convergence, DeviceState* __restrict__ st) {
+    if (st->done) return;
+    extern __shared__ __align__(128) unsigned char ess_smem[];
+    ess::ChainSmem& sm = *reinterpret_cast<ess::ChainSmem*>(ess_smem);
+    const unsigned v = blockIdx.x;
+    const float s = ess::chain(terms + (size_t)v * stride, summ + (size_t)v * nb_stride, n, sm, st->ess_stats[(PHASE == 2 ? 16 : 0) + v]);
+    if (threadIdx.x != 0) return;
+    st->ess_sums[(PHASE == 2 ? 16 : 0) + v] = s;
+    __threadfence();
+    if (atomicAdd(&st->ess_arrive, 1u) != (unsigned)(NV - 1)) return;      // the last CTA to arrive solves
+    __threadfence();
+    st->ess_arrive = 0u;
+    const volatile float* sums = st->ess_sums;
+    const int n_corr = (int)st->seq_count;
+    st->n_corr_last = n_corr;
+    if (n_corr < 3) { st->done = 1; return; }              // registration.cpp:361
+    float delta[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) delta[i] = (i % 5 == 0) ? 1.0f : 0.0f;
+    if (PHASE == 0) {
+        float A[36], nb[6], x[6];
+        int k = 0;
+        for (int a = 0; a < 6; ++a)
+            for (int b = a; b < 6; ++b) { const float val = sums[k++]; A[a * 6 + b] = val; A[b * 6 + a] = val; }
+        for (int a = 0; a < 6; ++a) nb[a] = -sums[21 + a];
+        ldlt6_solve(A, nb, x);                               // registration.cpp:366
+        Mat3 dR; euler_xyz_to_matrix(x[0], x[1], x[2], dR);  // registration.cpp:369-371
+        for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) delta[c * 4 + r] = dR(r, c); delta[12 + r] = x[3 + r]; }
+        icp_commit(st, delta, sums[27], n_corr, iter, n_src_f, stop_on_convergence);
+    } else if (PHASE == 1) {
+        const float nf = (float)n_corr;                      // means: sum / float(n), registration.cpp:380-381
+        for (int a = 0; a < 6; ++a) st->ess_means[a] = sums[a] / nf;
+    } else {
+        Mat3 H;
+        for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) H(a, b) = sums[16 + a * 3 + b];
+        Mat3 dR; rotation_from_cross_covariance(H, dR);      // registration.cpp:388-394
+        const float pm0 = st->ess_means[0], pm1 = st->ess_means[1], pm2 = st->ess_means[2];
+        float r0, r1, r2; mat3_vec(dR, pm0, pm1, pm2, r0, r1, r2);
+        for (int rr = 0; rr < 3; ++rr) for (int c2 = 0; c2 < 3; ++c2) delta[c2 * 4 + rr] = dR(rr, c2);
+        delta[12] = st->ess_means[3] - r0; delta[13] = st->ess_means[4] - r1; delta[14] = st->ess_means[5] - r2;     // registration.cpp:396
+        icp_commit(st, delta, sums[6], n_corr, iter, n_src_f, stop_on_convergence);
+    }
+}
+
 __global__ void icp_state_init_kernel(DeviceState* st, const float* __restrict__ T0) {
     int i = threadIdx.x;
     if (i < 16) { st->T[i] = T0[i]; st->res_T[i] = T0[i]; }
-    if (i == 0) { st->res_fitness = 0.0f; st->res_rmse = 0.0f; st->iterations = 0; st->done = 0; st->n_corr_last = 0; }
+    if (i == 0) { st->res_fitness = 0.0f; st->res_rmse = 0.0f; st->iterations = 0; st->done = 0; st->n_corr_last = 0; st->ess_arrive = 0u; st->seq_count = 0u; }
+    if (i < 32) { st->ess_stats[i][0] = 0u; st->ess_stats[i][1] = 0u; st->ess_stats[i][2] = 0u; st->ess_stats[i][3] = 0u; }
 }
 
 // ---------------------------------------------------------------------------------
@@ -957,12 +1088,34 @@ int icp_run_impl(b3d_ctx* c, const float* T0, float thr, int max_iter, int p2pla
     const float4* src = c->src4.as<float4>();
     const bool binned = n_src >= 16384;
     const unsigned seq_tiles = (unsigned)div_up(n_src, kScanTile);
-    const bool replay = plane ? c->icp_mode == 2 : c->icp_mode != 1;     // reference-order sequential sums
-    if (replay) {
+    // icp_mode 0 / 2 (default): sums in the reference's order, parallel and exact (b3d_ess.cuh); 1: fp64 tree sums (fast,
+    // order-free, tolerance-level); 3: the one-chain replay kernels (one dependent add per matched point; kept as an
+    // independent cross-check of the parallel form at sizes the CPU oracle cannot reach)
+    const bool tree = c->icp_mode == 1;
+    const bool legacy = c->icp_mode == 3;
+    const bool exact = !tree && !legacy;
+    const bool replay = legacy;
+    const size_t ess_stride = ess::padded_terms(n_src);
+    const unsigned ess_nb_stride = (unsigned)(ess_stride / ess::kBlock);
+    if (!tree) { B3D_CUDA(c, c->seq_rec.ensure(sizeof(float4) * n_src)); B3D_CUDA(c, c->seq_match.ensure(sizeof(uint32_t) * n_src)); }
+    if (legacy) {
         if (plane) B3D_CUDA(c, c->seq_N.ensure(sizeof(float4) * n_src));
-        B3D_CUDA(c, c->seq_rec.ensure(sizeof(float4) * n_src)); B3D_CUDA(c, c->seq_match.ensure(sizeof(uint32_t) * n_src));
         B3D_CUDA(c, c->seq_P.ensure(sizeof(float4) * n_src));   B3D_CUDA(c, c->seq_Q.ensure(sizeof(float4) * n_src));
         B3D_CUDA(c, c->scan_tmp.ensure(sizeof(unsigned) * (seq_tiles + 1)));
+    }
+    if (exact) {
+        static const cudaError_t smem_opt_in = [] {               // once per process: the chain kernels' TMA ring is larger than 48 KB
+            cudaError_t e = cudaFuncSetAttribute(icp_ess_chain_kernel<kAccPlane, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ess::ChainSmem));
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(icp_ess_chain_kernel<kAccPoint0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ess::ChainSmem));
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(icp_ess_chain_kernel<kAccPoint1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ess::ChainSmem));
+            return e;
+        }();
+        B3D_CUDA(c, smem_opt_in);
+        const size_t nv = plane ? kAccPlane : kAccPoint1;
+        B3D_CUDA(c, c->ess_terms.ensure(sizeof(float) * nv * ess_stride));
+        B3D_CUDA(c, c->ess_bsum.ensure(sizeof(double) * nv * ess_nb_stride));
+        B3D_CUDA(c, c->ess_guess.ensure(sizeof(double) * nv * (ess_stride / ess::kSuperTerms)));      // super-block sums
+        B3D_CUDA(c, c->ess_summ.ensure(sizeof(ess::BlockSummary) * nv * ess_nb_stride));
     }
     if (binned) {                                            // below that the reorder costs more than it saves
         StageTimer timer(c, 6);
@@ -978,7 +1131,7 @@ int icp_run_impl(b3d_ctx* c, const float* T0, float thr, int max_iter, int p2pla
         StageTimer timer(c, 5);
         const CellSlot* slots = c->grid_slots.as<CellSlot>();
         for (int iter = 0; iter < max_iter; ++iter) {
-            if (plane && !replay) {
+            if (plane && tree) {
                 B3D_CUDA(c, launch_dependent(icp_accumulate_kernel<true>, dim3(blocks), dim3(kIcpThreads), c->stream, src, n_src, (const DeviceState*)st, thr,
                                              slots, (const float4*)c->grid_pts.as<float4>(), (const CellSlot*)c->fine_slots.as<CellSlot>(),
                                              (const float4*)c->fine_pts.as<float4>(), (const float4*)c->tgt4.as<float4>(), (const float4*)c->nrm4.as<float4>(),
@@ -987,6 +1140,43 @@ int icp_run_impl(b3d_ctx* c, const float* T0, float thr, int max_iter, int p2pla
                 B3D_CUDA(c, launch_dependent(icp_update_kernel<true>, dim3(1), dim3(kUpdateThreads), c->stream, (const double*)c->partials.as<double>(), blocks, iter,
                                              (float)c->n_src, stop_on_conv, st));
                 B3D_LAUNCHED(c);
+            } else if (exact) {
+                // reference-order sums, parallel: search -> terms (+ fp64 block sums) -> guesses -> summaries -> chains + solve
+                if (binned) icp_search_kernel<true><<<blocks, kIcpThreads, 0, c->stream>>>(src, n_src, st, thr, slots, c->grid_pts.as<float4>(), c->fine_slots.as<CellSlot>(),
+                                                                                           c->fine_pts.as<float4>(), gp, c->seq_rec.as<float4>(), c->seq_match.as<uint32_t>(),
+                                                                                           c->tgt4.as<float4>(), cache, cache_idx);
+                else        icp_search_kernel<false><<<blocks, kIcpThreads, 0, c->stream>>>(src, n_src, st, thr, slots, c->grid_pts.as<float4>(), c->fine_slots.as<CellSlot>(),
+                                                                                            c->fine_pts.as<float4>(), gp, c->seq_rec.as<float4>(), c->seq_match.as<uint32_t>(),
+                                                                                           c->tgt4.as<float4>(), cache, cache_idx);
+                B3D_LAUNCHED(c);
+                float* terms = c->ess_terms.as<float>(); double* bsum = c->ess_bsum.as<double>(); double* ssum = c->ess_guess.as<double>();
+                ess::BlockSummary* summ = c->ess_summ.as<ess::BlockSummary>();
+                const int term_blocks = div_up(n_src, ess::kTermsThreads);
+                const unsigned summ_blocks = (unsigned)div_up(term_blocks, ess::kSummaryWarps);
+                if (plane) {
+                    PlaneTerms fn{c->seq_rec.as<float4>(), c->seq_match.as<uint32_t>(), c->tgt4.as<float4>(), c->nrm4.as<float4>()};
+                    ess::terms_kernel<kAccPlane><<<term_blocks, ess::kTermsThreads, 0, c->stream>>>(fn, n_src, &st->done, terms, ess_stride, bsum, ssum, &st->seq_count);
+                    B3D_LAUNCHED(c);
+                    ess::summary_kernel<<<dim3(summ_blocks, kAccPlane), ess::kSummaryWarps * 32, 0, c->stream>>>(terms, ess_stride, bsum, ssum, n_src, &st->done, summ);
+                    B3D_LAUNCHED(c);
+                    icp_ess_chain_kernel<kAccPlane, 0><<<kAccPlane, ess::kChainThreads, sizeof(ess::ChainSmem), c->stream>>>(terms, ess_stride, summ, ess_nb_stride, n_src, iter, (float)c->n_src, stop_on_conv, st);
+                    B3D_LAUNCHED(c);
+                } else {
+                    PointTerms0 fn0{c->seq_rec.as<float4>(), c->seq_match.as<uint32_t>(), c->tgt4.as<float4>()};
+                    ess::terms_kernel<kAccPoint0><<<term_blocks, ess::kTermsThreads, 0, c->stream>>>(fn0, n_src, &st->done, terms, ess_stride, bsum, ssum, &st->seq_count);
+                    B3D_LAUNCHED(c);
+                    ess::summary_kernel<<<dim3(summ_blocks, kAccPoint0), ess::kSummaryWarps * 32, 0, c->stream>>>(terms, ess_stride, bsum, ssum, n_src, &st->done, summ);
+                    B3D_LAUNCHED(c);
+                    icp_ess_chain_kernel<kAccPoint0, 1><<<kAccPoint0, ess::kChainThreads, sizeof(ess::ChainSmem), c->stream>>>(terms, ess_stride, summ, ess_nb_stride, n_src, iter, (float)c->n_src, stop_on_conv, st);
+                    B3D_LAUNCHED(c);
+                    PointTerms1 fn1{c->seq_rec.as<float4>(), c->seq_match.as<uint32_t>(), c->tgt4.as<float4>(), st};
+                    ess::terms_kernel<kAccPoint1><<<term_blocks, ess::kTermsThreads, 0, c->stream>>>(fn1, n_src, &st->done, terms, ess_stride, bsum, ssum, (unsigned*)nullptr);
+                    B3D_LAUNCHED(c);
+                    ess::summary_kernel<<<dim3(summ_blocks, kAccPoint1), ess::kSummaryWarps * 32, 0, c->stream>>>(terms, ess_stride, bsum, ssum, n_src, &st->done, summ);
+                    B3D_LAUNCHED(c);
+                    icp_ess_chain_kernel<kAccPoint1, 2><<<kAccPoint1, ess::kChainThreads, sizeof(ess::ChainSmem), c->stream>>>(terms, ess_stride, summ, ess_nb_stride, n_src, iter, (float)c->n_src, stop_on_conv, st);
+                    B3D_LAUNCHED(c);
+                }
             } else if (replay) {
                 // reference-order sums: search -> ordered compaction -> sequential replay (see icp_seq_p2p_kernel)
                 if (binned) icp_search_kernel<true><<<blocks, kIcpThreads, 0, c->stream>>>(src, n_src, st, thr, slots, c->grid_pts.as<float4>(), c->fine_slots.as<CellSlot>(),
@@ -1018,9 +1208,10 @@ int icp_run_impl(b3d_ctx* c, const float* T0, float thr, int max_iter, int p2pla
                 B3D_LAUNCHED(c);
             }
             // poll the device-side done flag now and then so converged runs stop launching
-            // a fixed-iteration request (no convergence break) of some length is known to be a long run: build the lists after the
-            // first two iterations (before that the queries are too far from the surface for the fine level to settle them)
-            const int lists_at = (!stop_on_conv && max_iter >= 2 * kListsAfter) ? 2 : kListsAfter;
+            // the second level pays for itself within a few iterations when the queries outnumber the targets (its build is
+            // O(27 n_tgt), a search O(n_src)): then build it after the first two iterations (before that the queries are too far
+            // from the surface for the fine level to settle them); otherwise only for calls still iterating after kListsAfter
+            const int lists_at = (max_iter >= 2 * kListsAfter && c->n_src >= 2 * c->n_tgt) ? 2 : kListsAfter;
             if (((iter & 15) == 15 || iter == lists_at - 1) && iter + 1 < max_iter) {
                 B3D_CUDA(c, cudaMemcpyAsync(&c->h_state->done, &st->done, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
                 B3D_CUDA(c, cudaStreamSynchronize(c->stream));

@@ -211,14 +211,15 @@ int b3d_register_depth(b3d_ctx* ctx, const uint16_t* depth, int width, int heigh
                        int ransac_max_iterations, float ransac_confidence, float icp_distance_threshold, int icp_max_iterations,
                        int point_to_plane, b3d_scene_result* out);
 
-/* Point-to-point accumulation: 0 (default) = add the matched pairs in source order in fp32, exactly
- * as src/registration.cpp:341, 374-386 does (bit-identical sums; one sequential dependency chain per
- * sum, so large clouds cost ~5 cycles per matched point per pass); 1 = deterministic fp64 tree sums
- * (fast; differs from the reference by the reference's own rounding noise, ~1e-4 in the final pose).
- * Point-to-plane uses the fp64 tree sums in modes 0 and 1 (they meet 1e-5 / 1e-6 m on well-conditioned
- * problems); 2 = reference order for point-to-plane as well (src/registration.cpp:343-354: ATA, ATb and
- * total_error added one matched point at a time) — bit-identical to the CPU path even where a threshold
- * close to the noise floor makes the iteration sensitive to the last bit of the sums. */
+/* How the ICP sums (ATA / ATb / total_error, src/registration.cpp:343-354; centroids and cross-covariance, :374-386) are
+ * accumulated.  0 (default; 2 is an alias): in the reference's order — one matched point at a time, source order, fp32 —
+ * reproduced bit for bit by a parallel exact-summation scheme (csrc/b3d_ess.cuh), for both error metrics.  This is what
+ * b3d_icp, b3d_register_scene and the C++ shim run: it holds the 1e-5 / 1e-6 m bar (in fact equality with the CPU
+ * path) even at the orchestrator's default threshold 0.4 * voxel (src/pipeline.cpp:104), which sits at the noise floor
+ * where the matched set flips with the last bit of the pose.  1 = deterministic fp64 tree sums: opt-in fast mode,
+ * order-free; within 1e-5 / 1e-6 m on well-conditioned thresholds, but up to ~1e-4 away at the noise floor and for
+ * point-to-point (the reference's own rounding noise).  3 = the reference order through one dependent add chain per sum
+ * (slow; an independent implementation kept to cross-check mode 0 at sizes the CPU oracle cannot reach). */
 int b3d_set_icp_mode(b3d_ctx* ctx, int mode);
 /* ICP on resident clouds. stop_on_convergence = 0 disables the |d rmse| < 1e-6 break
  * (src/registration.cpp:406) for fixed-iteration throughput runs. */
@@ -242,6 +243,12 @@ float b3d_stage_ms(const b3d_ctx* ctx, int stage);
 /* Number of 32-pair groups the last b3d_ransac_score call had to re-count with the reference
  * arithmetic because a pair fell inside the screening error band (diagnostic). */
 int b3d_score_recounts(b3d_ctx* ctx, uint64_t* out_groups);
+
+/* Exact-sum diagnostics of the last b3d_icp / b3d_icp_run call in a reference-order mode (3dvision_b200/csrc/b3d_ess.cuh):
+ * per running sum v < 32, out[4v] = walk rounds, out[4v+1] = 32-term blocks that had to be added term by term,
+ * out[4v+2] = SM cycles / 16 its chain took, accumulated over the call's iterations (sums 0-27: point-to-plane;
+ * 0-6 and 16-24: the two point-to-point passes). */
+int b3d_icp_exact_sum_stats(b3d_ctx* ctx, uint32_t out[128]);
 
 /* Measures the sustained issue rate of separate (un-fused) FMUL + FADD instructions on this
  * device, in lane-operations per second: the roofline denominator of the scoring kernel, whose

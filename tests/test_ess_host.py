@@ -1,0 +1,159 @@
+"""Exact-sequential-sum core (3dvision_b200/csrc/b3d_ess.cuh) against native in-order fp32 addition, on the CPU.
+
+The kernels that replay the reference's one-point-at-a-time sums (src/registration.cpp:341-358, 374-386, 270-279)
+skip the dependent add chain with precomputed integer block summaries; the result must be the same BITS as the chain.
+The header's arithmetic is host/device code, so the very same functions are compiled here with g++ and hammered with
+inputs built to hit every exit: binade changes, sign changes, exact ties, cancellation, huge/tiny/zero/non-finite terms."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "stubs", "ess_host_harness.cpp")
+HDR = os.path.join(HERE, "..", "3dvision_b200", "csrc", "b3d_ess.cuh")
+
+
+@pytest.fixture(scope="module")
+def ess(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("ess") / "libess_host.so")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-x", "c++", SRC, "-o", out], check=True)
+    lib = ctypes.CDLL(out)
+    fp = ctypes.POINTER(ctypes.c_float)
+    lib.ess_seq_sum.restype = ctypes.c_float
+    lib.ess_seq_sum.argtypes = [fp, ctypes.c_long]
+    lib.ess_parallel_sum.restype = ctypes.c_float
+    lib.ess_parallel_sum.argtypes = [fp, ctypes.c_long, ctypes.POINTER(ctypes.c_long)]
+    return lib
+
+
+def _both(lib, x):
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    p = x.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+    st = (ctypes.c_long * 3)()
+    a = np.float32(lib.ess_seq_sum(p, x.size))
+    b = np.float32(lib.ess_parallel_sum(p, x.size, st))
+    return a, b, tuple(st)
+
+
+def _same_bits(a, b):
+    return a.view(np.uint32) == b.view(np.uint32) or (np.isnan(a) and np.isnan(b))
+
+
+def test_header_is_the_product_header():
+    assert os.path.exists(HDR) and "block_summary" in open(HDR).read()
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 31, 32, 33, 1023, 1024, 1025, 4097, 300_000])
+def test_positive_terms_take_the_fast_path(ess, n):
+    rng = np.random.default_rng(n)
+    x = (rng.random(n, dtype=np.float32) ** 2) * np.float32(1e-6)          # like squared distances / J_a^2
+    a, b, st = _both(ess, x)
+    assert _same_bits(a, b)
+    if n >= 100_000:                                                       # monotone sum: ~20 binade changes in all
+        assert st[0] > 0.97 * (n // 32) and st[1] < 200
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_signed_random_walk(ess, seed):
+    rng = np.random.default_rng(100 + seed)
+    n = 200_000 + 37 * seed
+    x = rng.standard_normal(n).astype(np.float32) * np.float32(10.0 ** rng.integers(-6, 3))
+    a, b, st = _both(ess, x)
+    assert _same_bits(a, b)
+    assert st[0] > 0.8 * (n // 32)                                         # ties and binade changes included, most blocks fold
+
+
+def test_sum_returning_to_zero(ess):
+    rng = np.random.default_rng(7)
+    h = rng.standard_normal(50_000).astype(np.float32)
+    x = np.concatenate([h, -h[::-1], h[:5000]])                            # crosses zero, every binade twice
+    a, b, _ = _both(ess, x)
+    assert _same_bits(a, b)
+
+
+def test_exact_ties_and_power_of_two_terms(ess):
+    # terms that are exact half-ulps of the running sum: round-to-even depends on the sum's parity
+    x = np.empty(20_000, np.float32)
+    x[0] = 1.0
+    x[1:] = np.float32(2.0 ** -24)                                         # every add is a tie at first
+    a, b, _ = _both(ess, x)
+    assert _same_bits(a, b)
+    rng = np.random.default_rng(8)
+    x = (np.float32(2.0) ** rng.integers(-30, 4, 100_000)).astype(np.float32) * rng.choice(np.float32([1, -1, 1.5, 0.75]), 100_000)
+    a, b, _ = _both(ess, x)
+    assert _same_bits(a, b)
+
+
+def test_mixed_magnitudes_and_zeros(ess):
+    rng = np.random.default_rng(9)
+    n = 150_000
+    x = rng.standard_normal(n).astype(np.float32) * (np.float32(10.0) ** rng.integers(-12, 6, n).astype(np.float32))
+    x[rng.random(n) < 0.2] = 0.0
+    x[rng.random(n) < 0.01] = -0.0
+    a, b, _ = _both(ess, x)
+    assert _same_bits(a, b)
+
+
+def test_integer_valued_terms_are_all_ties_or_exact(ess):
+    rng = np.random.default_rng(10)
+    x = rng.integers(-3, 4, 400_000).astype(np.float32) * np.float32(0.5)  # sum grows past 2^24 * 0.5? no — stays exact
+    a, b, _ = _both(ess, x)
+    assert _same_bits(a, b)
+    x = np.full(40_000_0, 1.0, np.float32)
+    x[::3] = 16777216.0                                                    # jumps the sum where +1 becomes a tie / is lost
+    a, b, _ = _both(ess, x[:100_000])
+    assert _same_bits(a, b)
+
+
+def test_tiny_and_subnormal_sums(ess):
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal(50_000).astype(np.float32) * np.float32(1e-38)
+    a, b, _ = _both(ess, x)
+    assert _same_bits(a, b)
+    x = rng.standard_normal(50_000).astype(np.float32) * np.float32(1e-30)
+    a, b, _ = _both(ess, x)
+    assert _same_bits(a, b)
+
+
+def test_non_finite_terms(ess):
+    rng = np.random.default_rng(12)
+    for bad in (np.inf, -np.inf, np.nan, 3e38):
+        x = rng.random(10_000, dtype=np.float32)
+        x[5000] = bad
+        x[7000] = bad
+        a, b, _ = _both(ess, x)
+        assert _same_bits(a, b)
+
+
+def test_icp_like_normal_equation_terms(ess):
+    """Products J_a*J_b and J_a*r of a registration near convergence: the 28 sums of registration.cpp:343-354."""
+    rng = np.random.default_rng(13)
+    n = 120_000
+    p = rng.random((n, 3), dtype=np.float32) * np.float32(0.3)
+    nrm = rng.standard_normal((n, 3)).astype(np.float32)
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    J = np.concatenate([np.cross(p, nrm).astype(np.float32), nrm], axis=1)
+    r = (rng.standard_normal(n) * 5e-4).astype(np.float32)
+    fast = 0
+    for a_ in range(6):
+        for b_ in range(a_, 6):
+            s0, s1, st = _both(ess, J[:, a_] * J[:, b_])
+            assert _same_bits(s0, s1)
+            fast += st[0]
+        s0, s1, st = _both(ess, J[:, a_] * r)
+        assert _same_bits(s0, s1)
+    assert fast > 0
+
+
+def test_many_short_random_cases(ess):
+    rng = np.random.default_rng(14)
+    for _ in range(400):
+        n = int(rng.integers(1, 5000))
+        scale = np.float32(10.0 ** rng.integers(-8, 8))
+        bias = np.float32(rng.standard_normal() * rng.choice([0.0, 0.1, 1.0, 10.0]))
+        x = (rng.standard_normal(n).astype(np.float32) + bias) * scale
+        a, b, _ = _both(ess, x)
+        assert _same_bits(a, b)

@@ -110,6 +110,7 @@ def test_cuda_icp_golden(ctx, g):
     T, fit, rmse, iters = ctx.icp(c.source, c.target, c.target_normals, c.T_init, g["threshold"], g["max_iterations"], True)
     assert iters == g["iterations"] and fit == np.float32(g["fitness"])
     assert syn.rotation_error(T, T_of(g["T"])) < 1e-5 and syn.translation_error(T, T_of(g["T"])) < 1e-6
+    assert np.array_equal(T, T_of(g["T"])) and rmse == np.float32(g["rmse"])      # default mode adds in the reference's order
 
 
 @pytest.mark.gpu
@@ -125,5 +126,7 @@ def test_cuda_demo_scene_golden(ctx, demo):
     ctx.ransac_prepare(d["voxel"], DEMO["ransac_max_iterations"], DEMO["confidence"]); ctx.ransac_score()
     assert digest(ctx.ransac_counts()) == DEMO["sha256"]["counts"]
     Ti, fi, ri, iters = ctx.icp(d["src"], d["tgt"], d["tgt_n"], T, DEMO["icp_threshold"], 200, True)
+    # the orchestrator's own ICP call: threshold 0.4 * voxel (pipeline.cpp:104), default mode
     assert iters == DEMO["icp"]["iterations"] and fi == np.float32(DEMO["icp"]["fitness"])
     assert syn.rotation_error(Ti, T_of(DEMO["icp"]["T"])) < 1e-5 and syn.translation_error(Ti, T_of(DEMO["icp"]["T"])) < 1e-6
+    assert np.array_equal(Ti, T_of(DEMO["icp"]["T"])) and ri == np.float32(DEMO["icp"]["rmse"])

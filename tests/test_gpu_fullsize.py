@@ -3,7 +3,10 @@ test, so parity is checked (a) bit-exactly on bounded slices the oracle can affo
 ranges, source-point prefixes — every figure is independent per row / hypothesis / point), (b) between
 independent GPU kernels that share no screening arithmetic, and (c) through size-independent properties
 (determinism, permutation invariance, known ground truth)."""
+import hashlib
 import importlib
+import json
+import os
 import threading
 
 import numpy as np
@@ -83,16 +86,62 @@ def test_c2_icp_full_size(ctx, oracle, c2):
     assert kept.sum() > 2000
     assert np.array_equal(idx[:n][kept], ref.extra["nn_idx0"][kept]) and np.array_equal(d2[:n][kept], ref.extra["nn_d2_0"][kept])
     assert (idx[:n][~kept] == 0xFFFFFFFF).all()
+    # default mode = the reference's summation order: deterministic, and equal to the one-chain replay (mode 3, an
+    # independent kernel with one dependent add per matched point) after every one of the 50 iterations' worth of updates
     T, fit, rmse, it = ctx.icp_run(c2.T_init, c2.threshold, c2.iterations, True, False)
     T2, fit2, rmse2, _ = ctx.icp_run(c2.T_init, c2.threshold, c2.iterations, True, False)
-    assert np.array_equal(T, T2) and fit == fit2 and rmse == rmse2          # run-to-run deterministic (fixed-order sums)
+    assert np.array_equal(T, T2) and fit == fit2 and rmse == rmse2
     assert it == c2.iterations and fit > 0.99
     assert syn.rotation_error(T, c2.T_true) < 3e-4 and syn.translation_error(T, c2.T_true) < 5e-5
-    perm = np.random.default_rng(1).permutation(c2.source.shape[0])         # source order must not matter
-    ctx.set_clouds(c2.source[perm], c2.target, c2.target_normals)
-    T3, fit3, _, _ = ctx.icp_run(c2.T_init, c2.threshold, c2.iterations, True, False)
-    assert fit3 == fit and syn.rotation_error(T3, T) < 1e-6 and syn.translation_error(T3, T) < 1e-7
-    tperm = np.random.default_rng(2).permutation(c2.target.shape[0])        # target order only relabels indices
+    ctx.set_icp_mode(3)
+    try:
+        Tl, fitl, rmsel, _ = ctx.icp_run(c2.T_init, c2.threshold, 12, True, False)
+    finally:
+        ctx.set_icp_mode(0)
+    Td, fitd, rmsed, _ = ctx.icp_run(c2.T_init, c2.threshold, 12, True, False)
+    assert np.array_equal(Td, Tl) and fitd == fitl and rmsed == rmsel
+    # the production call (convergence break on) stops where the fixed-length run says it should and returns that state
+    Tp, fitp, rmsep, itp = ctx.icp_run(c2.T_init, c2.threshold, 200, True, True)
+    assert 2 <= itp < 200 and syn.rotation_error(Tp, c2.T_true) < 3e-4
+    Tq, _, rmseq, itq = ctx.icp_run(c2.T_init, c2.threshold, itp, True, False)
+    assert itq == itp and np.array_equal(Tp, Tq) and rmsep == rmseq
+
+
+def test_c2_icp_full_size_against_the_committed_oracle_iterations(ctx, c2):
+    """tests/golden/c2_icp_fullsize.json holds the CPU oracle's transform / fitness / rmse after 1 and 2 iterations of
+    configs[1] at FULL size (3e10 brute-force pair evaluations each — generated offline by make_golden_c2.py)."""
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "c2_icp_fullsize.json")))
+    dig = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+    assert dig(c2.source) == g["sha256"]["source"] and dig(c2.target) == g["sha256"]["target"]
+    assert dig(c2.target_normals) == g["sha256"]["normals"] and dig(c2.T_init) == g["sha256"]["T_init"]
+    ctx.set_clouds(c2.source, c2.target, c2.target_normals)
+    for iters, want in sorted(g["after"].items()):
+        T, fit, rmse, it = ctx.icp_run(c2.T_init, c2.threshold, int(iters), True, False)
+        Tw = np.asarray(want["T"], np.float32).reshape(4, 4)
+        assert it == want["iterations"] and fit == np.float32(want["fitness"])
+        assert syn.rotation_error(T, Tw) < 1e-5 and syn.translation_error(T, Tw) < 1e-6
+        assert np.array_equal(T, Tw) and rmse == np.float32(want["rmse"])
+
+
+def test_c2_icp_fast_mode_is_order_free(ctx, c2):
+    """b3d_set_icp_mode(1), fp64 tree sums: permuting the source does not move the result beyond fp64 rounding."""
+    ctx.set_icp_mode(1)
+    try:
+        ctx.set_clouds(c2.source, c2.target, c2.target_normals)
+        T, fit, rmse, it = ctx.icp_run(c2.T_init, c2.threshold, c2.iterations, True, False)
+        assert it == c2.iterations and fit > 0.99 and syn.rotation_error(T, c2.T_true) < 3e-4
+        perm = np.random.default_rng(1).permutation(c2.source.shape[0])
+        ctx.set_clouds(c2.source[perm], c2.target, c2.target_normals)
+        T3, fit3, _, _ = ctx.icp_run(c2.T_init, c2.threshold, c2.iterations, True, False)
+        assert fit3 == fit and syn.rotation_error(T3, T) < 1e-6 and syn.translation_error(T3, T) < 1e-7
+    finally:
+        ctx.set_icp_mode(0)
+
+
+def test_c2_target_order_only_relabels_indices(ctx, c2):
+    ctx.set_clouds(c2.source, c2.target, c2.target_normals)
+    idx, d2 = ctx.icp_nearest(c2.T_init, c2.threshold)
+    tperm = np.random.default_rng(2).permutation(c2.target.shape[0])
     ctx.set_clouds(c2.source, c2.target[tperm], c2.target_normals[tperm])
     idx_p, d2_p = ctx.icp_nearest(c2.T_init, c2.threshold)
     assert np.array_equal(d2_p, d2)
