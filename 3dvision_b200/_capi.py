@@ -25,13 +25,14 @@ NO_MATCH = 0xFFFFFFFF
 
 # every symbol include/b3d.h declares (tests check the library exports exactly these)
 SYMBOLS = [
+    "b3d_device_count",
     "b3d_cuda_available", "b3d_ctx_create", "b3d_ctx_destroy", "b3d_ctx_set_stream", "b3d_strerror", "b3d_last_error",
     "b3d_ransac", "b3d_icp",
     "b3d_set_clouds", "b3d_set_features", "b3d_set_match_mode", "b3d_match_features", "b3d_get_correspondences", "b3d_get_correspondences_dev", "b3d_set_correspondences",
     "b3d_correspondences_devptr", "b3d_set_score_mode", "b3d_ransac_prepare", "b3d_ransac_score", "b3d_ransac_reduce", "b3d_ransac_finish",
     "b3d_ransac_counts", "b3d_ransac_hypotheses", "b3d_set_icp_mode", "b3d_icp_run", "b3d_icp_nearest",
     "b3d_kernel_launches", "b3d_stage_ms", "b3d_measure_fp32_rate", "b3d_score_recounts", "b3d_icp_exact_sum_stats",
-    "b3d_prepare_model", "b3d_register_scene", "b3d_register_scene_device", "b3d_depth_to_cloud", "b3d_register_depth", "b3d_voxel_downsample", "b3d_set_voxel_order_mode", "b3d_estimate_normals", "b3d_compute_fpfh",
+    "b3d_prepare_model", "b3d_register_scene", "b3d_register_scene_device", "b3d_depth_to_cloud", "b3d_register_depth", "b3d_world_poses", "b3d_filter_duplicates", "b3d_voxel_downsample", "b3d_set_voxel_order_mode", "b3d_estimate_normals", "b3d_compute_fpfh",
 ]
 
 
@@ -110,10 +111,12 @@ def _declare(L):
     L.b3d_icp_exact_sum_stats.argtypes = [_vp, C.POINTER(C.c_uint32)]
     L.b3d_voxel_downsample.argtypes = [_vp, _vp, C.c_size_t, _vp, C.c_float, _vp, _vp, C.c_size_t, C.POINTER(C.c_size_t)]
     L.b3d_set_voxel_order_mode.argtypes = [_vp, C.c_int]
-    L.b3d_depth_to_cloud.argtypes = [_vp, _vp, C.c_int, C.c_int, _vp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _vp,
-                                     _vp, _vp, C.c_size_t, C.POINTER(C.c_size_t)]
-    L.b3d_register_depth.argtypes = [_vp, _vp, C.c_int, C.c_int, _vp] + [C.c_float] * 6 + [C.c_float, C.c_int, C.c_float, C.c_int, C.c_float,
-                                     C.c_float, C.c_int, C.c_int, C.POINTER(SceneResult)]
+    L.b3d_depth_to_cloud.argtypes = [_vp, _vp, C.c_int, C.c_int, _vp, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                                     C.c_float, _vp, _vp, _vp, C.c_size_t, C.POINTER(C.c_size_t)]
+    L.b3d_register_depth.argtypes = [_vp, _vp, C.c_int, C.c_int, _vp, C.c_int, C.c_int] + [C.c_float] * 6 + [C.c_float, C.c_int, C.c_float, C.c_int,
+                                     C.c_float, C.c_float, C.c_int, C.c_int, C.POINTER(SceneResult)]
+    L.b3d_world_poses.argtypes = [_vp, _vp, C.c_size_t, _vp, _vp]
+    L.b3d_filter_duplicates.argtypes = [_vp, _vp, C.c_size_t, C.c_float, _vp, C.POINTER(C.c_size_t)]
     L.b3d_register_scene_device.argtypes = [_vp, _vp, C.c_size_t, C.c_float, C.c_int, C.c_float, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int,
                                             C.POINTER(SceneResult)]
     L.b3d_prepare_model.argtypes = [_vp, _vp, C.c_size_t, C.c_float, C.c_int, C.c_float, C.POINTER(C.c_size_t)]
@@ -372,14 +375,34 @@ class Context:
                 "refined": (_T_from_colmajor(np.array(r.T, np.float32)), r.fitness, r.rmse, r.icp_iterations),
                 "n_source_points": int(r.n_source_points)}
 
+    def world_poses(self, refined_T, extrinsics=None) -> np.ndarray:
+        """pipeline.cpp:136-137 for a batch: (n,4,4) refined transforms -> extrinsics @ inverse (extrinsics None: the inverse)."""
+        T = np.asarray(refined_T, np.float32).reshape(-1, 4, 4)
+        flat = np.ascontiguousarray(np.stack([_T_colmajor(t) for t in T])) if len(T) else np.zeros((0, 16), np.float32)
+        ext = _T_colmajor(extrinsics) if extrinsics is not None else None
+        out = np.empty_like(flat)
+        self._check(self._L.b3d_world_poses(self._h, _ptr(flat), len(T), _ptr(ext), _ptr(out)))
+        return np.stack([_T_from_colmajor(o) for o in out]) if len(T) else np.zeros((0, 4, 4), np.float32)
+
+    def filter_duplicates(self, waypoints, min_distance: float) -> list:
+        """Pipeline::filterDuplicates, pipeline.cpp:153-180."""
+        T = np.asarray(waypoints, np.float32).reshape(-1, 4, 4)
+        if not len(T):
+            return []
+        flat = np.ascontiguousarray(np.stack([_T_colmajor(t) for t in T])); out = np.empty_like(flat); n = C.c_size_t()
+        self._check(self._L.b3d_filter_duplicates(self._h, _ptr(flat), len(T), float(min_distance), _ptr(out), C.byref(n)))
+        return [_T_from_colmajor(out[i]) for i in range(n.value)]
+
     def depth_to_cloud(self, depth, mask, scale_to_meters, clipping_max, fx, fy, cx, cy, bgr=None):
-        """pipeline.cpp:38-84. depth uint16 (h,w); mask uint8 (h,w) or None; bgr uint8 (h,w,3) or None -> (xyz, rgb or None)."""
+        """pipeline.cpp:38-84. depth uint16 (h,w); mask uint8 (any size: read through the reference's nearest-neighbour
+        resize, pipeline.cpp:39-41) or None; bgr uint8 (h,w,3) or None -> (xyz, rgb or None)."""
         depth = np.ascontiguousarray(depth, np.uint16); h, w = depth.shape
         mask = np.ascontiguousarray(mask, np.uint8) if mask is not None else None
+        mh, mw = mask.shape if mask is not None else (0, 0)
         bgr = np.ascontiguousarray(bgr, np.uint8) if bgr is not None else None
         xyz = np.empty((h * w, 3), np.float32); rgb = np.empty((h * w, 3), np.float32) if bgr is not None else None
         n = C.c_size_t()
-        self._check(self._L.b3d_depth_to_cloud(self._h, _ptr(depth), w, h, _ptr(mask), scale_to_meters, clipping_max, fx, fy, cx, cy, _ptr(bgr),
+        self._check(self._L.b3d_depth_to_cloud(self._h, _ptr(depth), w, h, _ptr(mask), mw, mh, scale_to_meters, clipping_max, fx, fy, cx, cy, _ptr(bgr),
                                                _ptr(xyz), _ptr(rgb), h * w, C.byref(n)))
         return xyz[:n.value].copy(), (rgb[:n.value].copy() if rgb is not None else None)
 
@@ -387,10 +410,11 @@ class Context:
                        ransac_max_iterations=100000, confidence=0.999, icp_threshold=None, icp_max_iterations=200, point_to_plane=True):
         depth = np.ascontiguousarray(depth, np.uint16); h, w = depth.shape
         mask = np.ascontiguousarray(mask, np.uint8) if mask is not None else None
+        mh, mw = mask.shape if mask is not None else (0, 0)
         radius = voxel_size * 5.0 if fpfh_radius is None else fpfh_radius
         thr = voxel_size * 0.4 if icp_threshold is None else icp_threshold
         r = SceneResult()
-        self._check(self._L.b3d_register_depth(self._h, _ptr(depth), w, h, _ptr(mask), scale_to_meters, clipping_max, fx, fy, cx, cy, voxel_size,
+        self._check(self._L.b3d_register_depth(self._h, _ptr(depth), w, h, _ptr(mask), mw, mh, scale_to_meters, clipping_max, fx, fy, cx, cy, voxel_size,
                                                int(normals_k), radius, int(ransac_max_iterations), confidence, thr, int(icp_max_iterations),
                                                int(bool(point_to_plane)), C.byref(r)))
         self._n_src = r.n_source_points; self._H = int(ransac_max_iterations)

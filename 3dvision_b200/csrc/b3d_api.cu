@@ -2,6 +2,7 @@
 // Thin: argument checks, H2D staging, stage sequencing.  All arithmetic of the path
 // runs in the CUDA kernels of b3d_match.cu / b3d_ransac.cu / b3d_icp.cu.
 #include "b3d_common.cuh"
+#include <atomic>
 #include <string.h>
 #include <new>
 
@@ -59,18 +60,29 @@ using namespace b3d;
 
 extern "C" {
 
+static bool device_is_sm100(int dev) {
+    int major = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) { cudaGetLastError(); return false; }
+    return major == 10;                     // the library carries sm_100a code only
+}
+
+int b3d_device_count(void) {
+    // leading run of sm_100 devices: contexts address devices by CUDA ordinal, so a foreign device in between ends the run
+    static std::atomic<int> cached{-1};
+    const int have = cached.load(std::memory_order_relaxed);
+    if (have > 0) return have;
+    if (!device_usable()) return 0;
+    int n = 0, usable = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    while (usable < n && device_is_sm100(usable)) ++usable;
+    if (usable > 0) cached.store(usable, std::memory_order_relaxed);
+    return usable;
+}
+
 int b3d_cuda_available(void) {
     // The orchestrator asks before every instance (src/pipeline.cpp:107) and cudaGetDeviceProperties costs milliseconds,
     // so a positive answer is remembered for the process; a negative one is re-probed (a device may appear later).
-    static int cached = 0;
-    if (cached) return 1;
-    if (!device_usable()) return 0;
-    int dev = 0, major = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return 0; }
-    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) { cudaGetLastError(); return 0; }
-    if (major != 10) return 0;              // the library carries sm_100a code only
-    cached = 1;
-    return 1;
+    return b3d_device_count() > 0 ? 1 : 0;
 }
 
 const char* b3d_strerror(int status) {
@@ -92,6 +104,7 @@ int b3d_ctx_create(int device, b3d_ctx** out) {
     if (!out) return B3D_ERR_INVALID;
     *out = nullptr;
     if (!device_usable()) return B3D_ERR_NO_DEVICE;
+    if (device < 0 || !device_is_sm100(device)) return B3D_ERR_NO_DEVICE;       // no such device, or not a Blackwell one
     if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return B3D_ERR_NO_DEVICE; }
     b3d_ctx* c = new (std::nothrow) b3d_ctx();
     if (!c) return B3D_ERR_ALLOC;
@@ -269,24 +282,36 @@ int b3d_register_scene_device(b3d_ctx* c, const float* scene_xyz_dev, size_t n, 
                                       icp_distance_threshold, icp_max_iterations, point_to_plane, out);
 }
 
-int b3d_depth_to_cloud(b3d_ctx* c, const uint16_t* depth, int width, int height, const uint8_t* mask_or_null, float scale_to_meters,
-                       float clipping_max, float fx, float fy, float cx, float cy, const uint8_t* bgr_or_null,
+int b3d_depth_to_cloud(b3d_ctx* c, const uint16_t* depth, int width, int height, const uint8_t* mask_or_null, int mask_width, int mask_height,
+                       float scale_to_meters, float clipping_max, float fx, float fy, float cx, float cy, const uint8_t* bgr_or_null,
                        float* out_xyz, float* out_rgb_or_null, size_t capacity, size_t* out_n) {
     if (!c || !depth || !out_xyz || !out_n) return B3D_ERR_INVALID;
     B3D_CUDA(c, enter(c));
-    return depth_to_cloud_impl(c, depth, width, height, mask_or_null, scale_to_meters, clipping_max, fx, fy, cx, cy, bgr_or_null,
-                               out_xyz, out_rgb_or_null, capacity, out_n);
+    return depth_to_cloud_impl(c, depth, width, height, mask_or_null, mask_width, mask_height, scale_to_meters, clipping_max, fx, fy, cx, cy,
+                               bgr_or_null, out_xyz, out_rgb_or_null, capacity, out_n);
 }
 
-int b3d_register_depth(b3d_ctx* c, const uint16_t* depth, int width, int height, const uint8_t* mask_or_null, float scale_to_meters,
-                       float clipping_max, float fx, float fy, float cx, float cy, float voxel_size, int normals_k, float fpfh_radius,
-                       int ransac_max_iterations, float ransac_confidence, float icp_distance_threshold, int icp_max_iterations,
-                       int point_to_plane, b3d_scene_result* out) {
+int b3d_register_depth(b3d_ctx* c, const uint16_t* depth, int width, int height, const uint8_t* mask_or_null, int mask_width, int mask_height,
+                       float scale_to_meters, float clipping_max, float fx, float fy, float cx, float cy, float voxel_size, int normals_k,
+                       float fpfh_radius, int ransac_max_iterations, float ransac_confidence, float icp_distance_threshold,
+                       int icp_max_iterations, int point_to_plane, b3d_scene_result* out) {
     if (!c || !depth || !out) return B3D_ERR_INVALID;
     B3D_CUDA(c, enter(c));
-    return register_depth_impl(c, depth, width, height, mask_or_null, scale_to_meters, clipping_max, fx, fy, cx, cy, voxel_size, normals_k,
-                               fpfh_radius, ransac_max_iterations, ransac_confidence, icp_distance_threshold, icp_max_iterations,
-                               point_to_plane, out);
+    return register_depth_impl(c, depth, width, height, mask_or_null, mask_width, mask_height, scale_to_meters, clipping_max, fx, fy, cx, cy,
+                               voxel_size, normals_k, fpfh_radius, ransac_max_iterations, ransac_confidence, icp_distance_threshold,
+                               icp_max_iterations, point_to_plane, out);
+}
+
+int b3d_world_poses(b3d_ctx* c, const float* refined_T, size_t n, const float extrinsics_or_null[16], float* out_T) {
+    if (!c || (n && (!refined_T || !out_T))) return B3D_ERR_INVALID;
+    B3D_CUDA(c, enter(c));
+    return world_poses_impl(c, refined_T, n, extrinsics_or_null, out_T);
+}
+
+int b3d_filter_duplicates(b3d_ctx* c, const float* poses, size_t n, float min_distance, float* out_poses, size_t* out_n) {
+    if (!c || !out_n || (n && (!poses || !out_poses))) return B3D_ERR_INVALID;
+    B3D_CUDA(c, enter(c));
+    return filter_duplicates_impl(c, poses, n, min_distance, out_poses, out_n);
 }
 
 int b3d_set_voxel_order_mode(b3d_ctx* c, int mode) {

@@ -838,9 +838,17 @@ int voxel_downsample_impl(b3d_ctx* c, const float* xyz, size_t n_, const float* 
 struct DepthImage {
     const unsigned short* depth; const unsigned char* mask; const unsigned char* bgr;
     int w; float inv_scale; float clip, fx, fy, cx, cy;
+    int mask_w, mask_h;          // mask size; when it differs from the depth image the mask is read through OpenCV's
+    double ifx, ify;             // nearest-neighbour resize map (pipeline.cpp:39-41): sx = min(floor(x * ifx), mask_w - 1)
+    __device__ unsigned char mask_at(unsigned px) const {
+        if (ifx == 1.0 && ify == 1.0) return mask[px];
+        const int u = (int)(px % (unsigned)w), v = (int)(px / (unsigned)w);
+        const int sx = min((int)floor((double)u * ifx), mask_w - 1), sy = min((int)floor((double)v * ify), mask_h - 1);
+        return mask[(size_t)sy * (size_t)mask_w + (size_t)sx];
+    }
     __device__ float z_at(unsigned px) const {
         float z = (float)depth[px] * inv_scale;                                     // convertTo(CV_32FC1, 1.0 / scale): OpenCV scales 16u -> 32f in float
-        if (mask && !(mask[px] > 10)) z = 0.0f;                                     // threshold(mask, 10) ; setTo(0, mask == 0)
+        if (mask && !(mask_at(px) > 10)) z = 0.0f;                                  // threshold(mask, 10) ; setTo(0, mask == 0)
         return z;
     }
 };
@@ -866,18 +874,23 @@ struct PixelEmit {                       // stable compaction: output order is t
 };
 
 // device core: host images in, packed xyz (and rgb) left in fbuf[F_IMG_XYZ] / fbuf[F_IMG_RGB]; *n_out points
-static int depth_to_cloud_dev(b3d_ctx* c, const uint16_t* depth, int w, int h, const uint8_t* mask, float scale, float clip,
+static int depth_to_cloud_dev(b3d_ctx* c, const uint16_t* depth, int w, int h, const uint8_t* mask, int mask_w, int mask_h, float scale, float clip,
                               float fx, float fy, float cx, float cy, const uint8_t* bgr, unsigned* n_out) {
     const size_t px = (size_t)w * (size_t)h;
+    if (mask && (mask_w <= 0 || mask_h <= 0)) { mask_w = w; mask_h = h; }          // 0 x 0: the mask has the depth image's size
+    const size_t mpx = mask ? (size_t)mask_w * (size_t)mask_h : 0;
+    if (mpx > 0x7FFFFFFFu) return fail(c, B3D_ERR_INVALID, "depth_to_cloud: bad mask size");
     B3D_CUDA(c, c->fbuf[F_IMG_DEPTH].ensure(px * 2)); B3D_CUDA(c, c->fbuf[F_IMG_XYZ].ensure(px * 12));
     B3D_CUDA(c, cudaMemcpyAsync(c->fbuf[F_IMG_DEPTH].p, depth, px * 2, cudaMemcpyHostToDevice, c->stream));
-    if (mask) { B3D_CUDA(c, c->fbuf[F_IMG_MASK].ensure(px)); B3D_CUDA(c, cudaMemcpyAsync(c->fbuf[F_IMG_MASK].p, mask, px, cudaMemcpyHostToDevice, c->stream)); }
+    if (mask) { B3D_CUDA(c, c->fbuf[F_IMG_MASK].ensure(mpx)); B3D_CUDA(c, cudaMemcpyAsync(c->fbuf[F_IMG_MASK].p, mask, mpx, cudaMemcpyHostToDevice, c->stream)); }
     if (bgr) {
         B3D_CUDA(c, c->fbuf[F_IMG_BGR].ensure(px * 3)); B3D_CUDA(c, c->fbuf[F_IMG_RGB].ensure(px * 12));
         B3D_CUDA(c, cudaMemcpyAsync(c->fbuf[F_IMG_BGR].p, bgr, px * 3, cudaMemcpyHostToDevice, c->stream));
     }
     DepthImage im{c->fbuf[F_IMG_DEPTH].as<unsigned short>(), mask ? c->fbuf[F_IMG_MASK].as<unsigned char>() : nullptr,
-                  bgr ? c->fbuf[F_IMG_BGR].as<unsigned char>() : nullptr, w, (float)(1.0 / (double)scale), clip, fx, fy, cx, cy};
+                  bgr ? c->fbuf[F_IMG_BGR].as<unsigned char>() : nullptr, w, (float)(1.0 / (double)scale), clip, fx, fy, cx, cy,
+                  mask ? mask_w : w, mask ? mask_h : h,
+                  mask ? 1.0 / ((double)w / (double)mask_w) : 1.0, mask ? 1.0 / ((double)h / (double)mask_h) : 1.0};      // cv::resize: ifx = 1 / (dst_w / src_w)
     PixelKept kept{im}; PixelEmit emit{im, c->fbuf[F_IMG_XYZ].as<float>(), bgr ? c->fbuf[F_IMG_RGB].as<float>() : nullptr};
     const unsigned tiles = (unsigned)div_up((long long)px, kScanTile);
     B3D_CUDA(c, c->scan_tmp.ensure(sizeof(unsigned) * (tiles + 2)));
@@ -893,14 +906,14 @@ static int depth_to_cloud_dev(b3d_ctx* c, const uint16_t* depth, int w, int h, c
     return B3D_OK;
 }
 
-int depth_to_cloud_impl(b3d_ctx* c, const uint16_t* depth, int w, int h, const uint8_t* mask, float scale, float clip,
+int depth_to_cloud_impl(b3d_ctx* c, const uint16_t* depth, int w, int h, const uint8_t* mask, int mask_w, int mask_h, float scale, float clip,
                         float fx, float fy, float cx, float cy, const uint8_t* bgr, float* out_xyz, float* out_rgb, size_t capacity, size_t* out_n) {
     *out_n = 0;
     if (w <= 0 || h <= 0 || (size_t)w * (size_t)h > 0x7FFFFFFFu) return fail(c, B3D_ERR_INVALID, "depth_to_cloud: bad image size");
     if (!(scale > 0.0f)) return fail(c, B3D_ERR_INVALID, "depth_to_cloud: scale_to_meters must be positive");
     if (bgr && !out_rgb) return fail(c, B3D_ERR_INVALID, "depth_to_cloud: colour image given but no output for it");
     unsigned n = 0;
-    int rc = depth_to_cloud_dev(c, depth, w, h, mask, scale, clip, fx, fy, cx, cy, bgr, &n);
+    int rc = depth_to_cloud_dev(c, depth, w, h, mask, mask_w, mask_h, scale, clip, fx, fy, cx, cy, bgr, &n);
     if (rc != B3D_OK) return rc;
     *out_n = n;
     if (n > capacity) return fail(c, B3D_ERR_INVALID, "depth_to_cloud: output capacity too small (out_n holds the size needed)");
@@ -964,14 +977,14 @@ int register_scene_device_impl(b3d_ctx* c, const float* xyz_dev, size_t n, float
 }
 
 // depth image + mask of one instance -> pose: Pipeline::processInstance (pipeline.cpp:38-129) up to the refined transform
-int register_depth_impl(b3d_ctx* c, const uint16_t* depth, int w, int h, const uint8_t* mask, float scale, float clip, float fx, float fy,
+int register_depth_impl(b3d_ctx* c, const uint16_t* depth, int w, int h, const uint8_t* mask, int mask_w, int mask_h, float scale, float clip, float fx, float fy,
                         float cx, float cy, float voxel, int k, float radius, int ransac_iterations, float confidence, float icp_threshold,
                         int icp_iterations, int point_to_plane, b3d_scene_result* out) {
     if (!c->model_ready) return fail(c, B3D_ERR_STATE, "register_depth: call b3d_prepare_model first");
     if (w <= 0 || h <= 0 || (size_t)w * (size_t)h > 0x7FFFFFFFu) return fail(c, B3D_ERR_INVALID, "register_depth: bad image size");
     if (!(scale > 0.0f)) return fail(c, B3D_ERR_INVALID, "register_depth: scale_to_meters must be positive");
     unsigned n = 0;
-    int rc = depth_to_cloud_dev(c, depth, w, h, mask, scale, clip, fx, fy, cx, cy, nullptr, &n);
+    int rc = depth_to_cloud_dev(c, depth, w, h, mask, mask_w, mask_h, scale, clip, fx, fy, cx, cy, nullptr, &n);
     if (rc != B3D_OK) return rc;
     return register_resident(c, c->fbuf[F_IMG_XYZ].as<float>(), true, n, voxel, k, radius, ransac_iterations, confidence, icp_threshold,
                              icp_iterations, point_to_plane, out);

@@ -307,12 +307,15 @@ B3D_HD void ldlt6_solve(const float* A, const float* b, float* x) {
 // ---- Rx(a) Ry(b) Rz(g) through unit quaternions (AngleAxis products are Quaternion
 // products in Eigen; .matrix() is Quaternion::toRotationMatrix()) ---------------------
 struct Quat { float w, x, y, z; };
+// Coefficient order of Eigen 3.4's SSE quat_product (Geometry/arch/Geometry_SIMD.h), which is what a default x86-64 build
+// of the reference runs for Quaternionf * Quaternionf: (a * b.wwww - a.zxyx * b.yzxx) + (a.yzxz * b.zxyz + a.wwwy * b.xyzy),
+// the w lane with its second parenthesis negated.
 B3D_HD Quat quat_mul(Quat a, Quat b) {
     Quat r;
-    r.w = a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z;
-    r.x = a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y;
-    r.y = a.w * b.y + a.y * b.w + a.z * b.x - a.x * b.z;
-    r.z = a.w * b.z + a.z * b.w + a.x * b.y - a.y * b.x;
+    r.x = (a.x * b.w - a.z * b.y) + (a.y * b.z + a.w * b.x);
+    r.y = (a.y * b.w - a.x * b.z) + (a.z * b.x + a.w * b.y);
+    r.z = (a.z * b.w - a.y * b.x) + (a.x * b.y + a.w * b.z);
+    r.w = (a.w * b.w - a.x * b.x) + (-(a.z * b.z + a.y * b.y));
     return r;
 }
 B3D_HD void euler_xyz_to_matrix(float ax, float ay, float az, Mat3& R) {

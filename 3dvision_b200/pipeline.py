@@ -21,7 +21,7 @@ from dataclasses import dataclass
 
 import numpy as np
 
-from .registration import (FPFHFeatures, GPURegistration, PointCloud, Registration, RegistrationResult)
+from .registration import (FPFHFeatures, GPURegistration, PointCloud, Registration, RegistrationResult, _context)
 
 
 @dataclass
@@ -55,33 +55,24 @@ def process_instance(inst: Instance) -> tuple[RegistrationResult, RegistrationRe
 
 def world_pose(refined_transformation, camera_extrinsics=None):
     """pipeline.cpp:136-137: T_camera_object = refined^-1; T_world_object = extrinsics * T_camera_object.
-    Orchestrator-side 4x4 algebra on the host (O(1) per instance, not a device stage); float32 like the reference, but
-    Eigen's 4x4 inverse kernel is not restated, so the last bits may differ from the reference's."""
-    Tco = np.linalg.inv(np.asarray(refined_transformation, np.float32)).astype(np.float32)
-    if camera_extrinsics is None:
-        return Tco
-    return (np.asarray(camera_extrinsics, np.float32) @ Tco).astype(np.float32)
+    Runs in libb3d.so (``b3d_world_poses``): Eigen's SSE 4x4 inverse kernel and packet product order, on the calling
+    thread's context like every other stage."""
+    return _context().world_poses(np.asarray(refined_transformation, np.float32).reshape(1, 4, 4), camera_extrinsics)[0]
+
+
+def world_poses(refined_transformations, camera_extrinsics=None):
+    """world_pose for a batch of refined transforms in one call: (n,4,4) -> (n,4,4)."""
+    return _context().world_poses(refined_transformations, camera_extrinsics)
 
 
 def filter_duplicates(waypoints, min_distance: float):
     """Pipeline::filterDuplicates (pipeline.cpp:153-180): greedy de-duplication of the per-instance poses by the distance
     between their translations; of two poses closer than min_distance the one nearer the origin is kept, in the slot of
-    the first."""
-    kept = []
-    for wp in waypoints:
-        wp = np.asarray(wp, np.float32)
-        pos = wp[:3, 3]
-        dup = False
-        for i, other in enumerate(kept):
-            d = pos - other[:3, 3]
-            if np.float32(np.sqrt(np.float32(d[0] * d[0] + np.float32(d[1] * d[1] + d[2] * d[2])))) < np.float32(min_distance):
-                dup = True
-                if np.linalg.norm(pos) < np.linalg.norm(other[:3, 3]):
-                    kept[i] = wp
-                break
-        if not dup:
-            kept.append(wp)
-    return kept
+    the first.  Runs in libb3d.so (``b3d_filter_duplicates``)."""
+    waypoints = list(waypoints)
+    if not waypoints:
+        return []
+    return _context().filter_duplicates(np.stack([np.asarray(w, np.float32).reshape(4, 4) for w in waypoints]), min_distance)
 
 
 _pools: dict[int, ThreadPoolExecutor] = {}

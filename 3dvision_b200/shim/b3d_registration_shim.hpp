@@ -25,6 +25,8 @@
 #pragma once
 
 #include <array>
+#include <atomic>
+#include <cstdlib>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -38,21 +40,39 @@ static_assert(sizeof(Eigen::Vector3f) == 3 * sizeof(float), "Eigen::Vector3f mus
 static_assert(sizeof(std::array<float, B3D_DESC_DIM>) == B3D_DESC_DIM * sizeof(float), "descriptor rows must be 33 packed floats");
 static_assert(sizeof(Eigen::Matrix4f) == 16 * sizeof(float), "Eigen::Matrix4f must be 16 floats (column-major)");
 
-inline int& device_index() { static int dev = 0; return dev; }
+// Which GPU a host thread's context lives on.  The reference's unit of parallelism is its worker pool
+// (src/pipeline.cpp:16, 321-327; include/thread_pool.hpp): every pool thread that first calls into the shim is dealt
+// the next usable sm_100 device round-robin, so a pool of num_threads workers spreads over all the GPUs of the box
+// (instances are independent: no collective is needed, SURVEY.md 8e "batched multi-object").  device_index() >= 0 pins
+// every new thread context to that device instead (set it before the first call, or export B3D_DEVICE).
+inline int& device_index() {
+    static int dev = [] { const char* e = std::getenv("B3D_DEVICE"); return e ? std::atoi(e) : -1; }();
+    return dev;
+}
+inline int next_device() {
+    if (device_index() >= 0) return device_index();
+    static std::atomic<unsigned> dealt{0};
+    const int n = b3d_device_count();
+    return n > 0 ? (int)(dealt.fetch_add(1u) % (unsigned)n) : 0;
+}
 
 struct ThreadContext {
     b3d_ctx* ctx = nullptr;
+    int device = -1;
     ~ThreadContext() { if (ctx) b3d_ctx_destroy(ctx); }
 };
+inline ThreadContext& thread_context() { thread_local ThreadContext tc; return tc; }
 
 inline b3d_ctx* context() {
-    thread_local ThreadContext tc;
+    ThreadContext& tc = thread_context();
     if (!tc.ctx) {
-        int rc = b3d_ctx_create(device_index(), &tc.ctx);
+        tc.device = next_device();
+        int rc = b3d_ctx_create(tc.device, &tc.ctx);
         if (rc != B3D_OK) throw std::runtime_error(std::string("b3d: ") + b3d_strerror(rc));
     }
     return tc.ctx;
 }
+inline int context_device() { context(); return thread_context().device; }
 
 inline void check(b3d_ctx* ctx, int rc) {
     if (rc != B3D_OK) {
@@ -130,6 +150,24 @@ inline RegistrationResult gpuIcpRefine(const PointCloud& source, const PointClou
                                        float distance_threshold, int max_iterations = 200) {
     if (!isCudaAvailable()) throw std::runtime_error("CUDA not available");      // src/gpu_impl.cpp:258
     return icpRefine(source, target, initial_transform, distance_threshold, max_iterations, true);
+}
+
+// ---- pose post-processing of Pipeline::processInstance / Pipeline::filterDuplicates (src/pipeline.cpp:136-137, 153-180) ----
+// T_world_object = camera_extrinsics * refined.transformation.inverse()
+inline Eigen::Matrix4f worldPose(const Eigen::Matrix4f& camera_extrinsics, const Eigen::Matrix4f& refined_transformation) {
+    b3d_ctx* ctx = context();
+    Eigen::Matrix4f out;
+    check(ctx, b3d_world_poses(ctx, refined_transformation.data(), 1, camera_extrinsics.data(), out.data()));
+    return out;
+}
+inline std::vector<Eigen::Matrix4f> filterDuplicates(const std::vector<Eigen::Matrix4f>& waypoints, float min_distance) {
+    b3d_ctx* ctx = context();
+    std::vector<Eigen::Matrix4f> filtered(waypoints.size());
+    size_t kept = 0;
+    check(ctx, b3d_filter_duplicates(ctx, waypoints.empty() ? nullptr : waypoints.front().data(), waypoints.size(), min_distance,
+                                     filtered.empty() ? nullptr : filtered.front().data(), &kept));
+    filtered.resize(kept);
+    return filtered;
 }
 
 }  // namespace b3d_shim

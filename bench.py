@@ -324,6 +324,8 @@ def run_ours(args):
         line["also"].update(secondary(ctx, b3d, syn, case, flush))
         # same call with bail-out scoring (b3d_set_score_mode 3): identical winner / transform / fitness / rmse,
         # hypotheses that provably cannot reach the best full count are dropped part-way
+        ctx.set_clouds_device(d_src.data_ptr(), N_SRC, d_tgt.data_ptr(), None, N_TGT)     # secondary() re-used the context
+        ctx.set_features_device(d_sd.data_ptr(), d_td.data_ptr())
         ctx.set_score_mode(3)
         for _ in range(2):
             rb = step_resident()

@@ -50,6 +50,10 @@ typedef enum b3d_status {
  * 1 if a CUDA device with compute capability 10.x is usable, else 0. Never fails. */
 int b3d_cuda_available(void);
 
+/* Number of usable devices: CUDA devices 0 .. n-1 of this process with compute capability 10.x (the library carries
+ * sm_100a code only).  0 if there is none.  Device ordinals are CUDA's (CUDA_VISIBLE_DEVICES applies). */
+int b3d_device_count(void);
+
 /* Creates a context on `device` (stream + persistent workspace; no cudaMalloc on
  * the steady-state call path).  Replaces the per-call cudaMalloc/cudaFree block of
  * GPURegistration::icpRefine, src/gpu_impl.cpp:155-186, 246-255. */
@@ -200,16 +204,28 @@ int b3d_register_scene_device(b3d_ctx* ctx, const float* scene_xyz_dev, size_t n
  * GPUDepth::preprocess + GPUPointCloud::generate, include/gpu_depth.hpp:9-22, do on the reference's GPU branch, but in
  * the CPU branch's raster order): z = float(depth) * float(1 / scale_to_meters) (OpenCV's 16u -> 32f convertTo); zero where mask <= 10 (mask_or_null == NULL: no
  * masking); keep 0 < z <= clipping_max; x = (u - cx) z / fx, y = (v - cy) z / fy; rgb = bgr reversed / 255.
- * Mask and colour image must have the depth image's size (the reference's nearest-neighbour mask resize is not done
- * here).  capacity / out_n as in b3d_voxel_downsample (width*height always suffices). */
-int b3d_depth_to_cloud(b3d_ctx* ctx, const uint16_t* depth, int width, int height, const uint8_t* mask_or_null, float scale_to_meters,
-                       float clipping_max, float fx, float fy, float cx, float cy, const uint8_t* bgr_or_null,
+ * mask_width x mask_height is the mask's own size (0 x 0: the depth image's size); when it differs the mask is read
+ * through OpenCV's nearest-neighbour resize map, cv::resize(mask, ..., depth.size(), 0, 0, INTER_NEAREST) of
+ * src/pipeline.cpp:39-41 (source pixel min(floor(x / (width / (double)mask_width)), mask_width - 1)).  The colour image
+ * must have the depth image's size.  capacity / out_n as in b3d_voxel_downsample (width*height always suffices). */
+int b3d_depth_to_cloud(b3d_ctx* ctx, const uint16_t* depth, int width, int height, const uint8_t* mask_or_null, int mask_width, int mask_height,
+                       float scale_to_meters, float clipping_max, float fx, float fy, float cx, float cy, const uint8_t* bgr_or_null,
                        float* out_xyz, float* out_rgb_or_null, size_t capacity, size_t* out_n);
 /* b3d_depth_to_cloud followed by b3d_register_scene without the cloud leaving the device: src/pipeline.cpp:38-129. */
-int b3d_register_depth(b3d_ctx* ctx, const uint16_t* depth, int width, int height, const uint8_t* mask_or_null, float scale_to_meters,
-                       float clipping_max, float fx, float fy, float cx, float cy, float voxel_size, int normals_k, float fpfh_radius,
-                       int ransac_max_iterations, float ransac_confidence, float icp_distance_threshold, int icp_max_iterations,
-                       int point_to_plane, b3d_scene_result* out);
+int b3d_register_depth(b3d_ctx* ctx, const uint16_t* depth, int width, int height, const uint8_t* mask_or_null, int mask_width, int mask_height,
+                       float scale_to_meters, float clipping_max, float fx, float fy, float cx, float cy, float voxel_size, int normals_k,
+                       float fpfh_radius, int ransac_max_iterations, float ransac_confidence, float icp_distance_threshold,
+                       int icp_max_iterations, int point_to_plane, b3d_scene_result* out);
+
+/* ---- pose post-processing of the orchestrator ---------------------------------------------
+ * src/pipeline.cpp:136-137 for n refined poses at once: out[i] = camera_extrinsics * refined_T[i].inverse()
+ * (extrinsics_or_null == NULL: the inverse, T_camera_object, alone).  All matrices float[16] column-major, packed.
+ * Matrix4f::inverse() follows Eigen 3.4's SSE kernel operation for operation, the product its packet order. */
+int b3d_world_poses(b3d_ctx* ctx, const float* refined_T, size_t n, const float extrinsics_or_null[16], float* out_T);
+/* Pipeline::filterDuplicates(waypoints, min_distance), src/pipeline.cpp:153-180: walks the n poses in order; a pose whose
+ * translation is closer than min_distance to a pose kept so far is dropped, or takes that pose's slot if it is nearer
+ * the origin.  out holds n poses at most; *out_n = number kept. */
+int b3d_filter_duplicates(b3d_ctx* ctx, const float* poses, size_t n, float min_distance, float* out_poses, size_t* out_n);
 
 /* How the ICP sums (ATA / ATb / total_error, src/registration.cpp:343-354; centroids and cross-covariance, :374-386) are
  * accumulated.  0 (default; 2 is an alias): in the reference's order — one matched point at a time, source order, fp32 —

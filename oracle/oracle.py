@@ -23,7 +23,7 @@ _lib = None
 
 def build(force: bool = False) -> str:
     """Compile oracle/_build/liboracle.so with the committed Makefile."""
-    srcs = [os.path.join(_HERE, f) for f in ("registration_oracle.cpp", "pipeline_inputs.cpp", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("registration_oracle.cpp", "pipeline_inputs.cpp", "pose_post.cpp", "Makefile")]
     stale = force or not os.path.exists(_LIB_PATH) or any(
         os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs if os.path.exists(s))
     if stale:
@@ -39,6 +39,25 @@ def lib():
         _lib = C.CDLL(_LIB_PATH)
         _declare(_lib)
     return _lib
+
+
+class use_library:
+    """Context manager: route every call of this module to another build of the restatement (the variant libraries of
+    `make -C oracle variants`, used by oracle/sensitivity.py)."""
+
+    def __init__(self, path: str):
+        self.path = path
+
+    def __enter__(self):
+        global _lib
+        self.prev = _lib
+        _lib = C.CDLL(self.path)
+        _declare(_lib)
+        return _lib
+
+    def __exit__(self, *exc):
+        global _lib
+        _lib = self.prev
 
 
 _f32p = C.POINTER(C.c_float)
@@ -74,6 +93,11 @@ def _declare(L):
     L.orc_voxel_downsample.restype = C.c_size_t
     L.orc_estimate_normals.argtypes = [_f32p, C.c_size_t, C.c_int, _f32p]
     L.orc_compute_fpfh.argtypes = [_f32p, _f32p, C.c_size_t, C.c_float, _f32p]
+    L.orc_mat4_inverse.argtypes = [_f32p, _f32p]
+    L.orc_world_pose.argtypes = [_f32p, _f32p, _f32p]
+    L.orc_filter_duplicates.argtypes = [_f32p, C.c_size_t, C.c_float, _f32p]
+    L.orc_filter_duplicates.restype = C.c_size_t
+    L.orc_resize_mask_nearest.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
 
 
 def _f32(a, shape=None):
@@ -257,3 +281,38 @@ def depth_to_cloud(depth, mask, scale_to_meters, clipping_max, fx, fy, cx, cy, b
     n = f(depth.ctypes.data, w, h, mask.ctypes.data if mask is not None else None, scale_to_meters, clipping_max, fx, fy, cx, cy,
           bgr.ctypes.data if bgr is not None else None, xyz.ctypes.data, rgb.ctypes.data if rgb is not None else None)
     return xyz[:n].copy(), (rgb[:n].copy() if rgb is not None else None)
+
+
+# ---- pose post-processing and mask resize around the hot path (pipeline.cpp:38-41, 136-137, 153-180) ----
+def mat4_inverse(M) -> np.ndarray:
+    """Eigen::Matrix4f::inverse() (SSE 2x2-block kernel restated)."""
+    out = np.empty(16, np.float32)
+    lib().orc_mat4_inverse(_p(_T_to_colmajor(M)), _p(out))
+    return _T_from_colmajor(out)
+
+
+def world_pose(refined_T, extrinsics=None) -> np.ndarray:
+    """pipeline.cpp:136-137: extrinsics * refined.transformation.inverse() (extrinsics None -> the inverse alone)."""
+    out = np.empty(16, np.float32)
+    ext = _T_to_colmajor(extrinsics) if extrinsics is not None else None
+    lib().orc_world_pose(_p(ext), _p(_T_to_colmajor(refined_T)), _p(out))
+    return _T_from_colmajor(out)
+
+
+def filter_duplicates(waypoints, min_distance: float) -> list:
+    """Pipeline::filterDuplicates, pipeline.cpp:153-180."""
+    wps = [np.asarray(w, np.float32).reshape(4, 4) for w in waypoints]
+    if not wps:
+        return []
+    flat = np.ascontiguousarray(np.stack([_T_to_colmajor(w) for w in wps]))
+    out = np.empty_like(flat)
+    n = lib().orc_filter_duplicates(_p(flat), len(wps), min_distance, _p(out))
+    return [_T_from_colmajor(out[i]) for i in range(n)]
+
+
+def resize_mask_nearest(mask, dst_w: int, dst_h: int) -> np.ndarray:
+    """cv::resize(mask, ..., depth.size(), 0, 0, INTER_NEAREST), pipeline.cpp:39-41."""
+    mask = np.ascontiguousarray(mask, np.uint8); sh, sw = mask.shape
+    out = np.empty((dst_h, dst_w), np.uint8)
+    lib().orc_resize_mask_nearest(mask.ctypes.data, sw, sh, dst_w, dst_h, out.ctypes.data)
+    return out

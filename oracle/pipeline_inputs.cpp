@@ -10,7 +10,7 @@
 //   estimateNormals (+findKNN)        src/registration.cpp:63-81, 105-130
 //   computeFPFH (+findRadiusNN)       src/registration.cpp:83-102, 133-201
 // These stages are OUT of the round-1 hot-path scope (SURVEY.md §8f rows
-// f-1..f-4); nothing here is a parity target yet.  Eigen's
+// f-1..f-4); every function here is a parity target of the widened path.  Eigen's
 // SelfAdjointEigenSolver<Matrix3f> is restated from the Eigen 3.4.0 algorithm
 // (scaled tridiagonalisation + implicit symmetric QR) — "parity unpinned".
 // Build: g++ -O2 -std=c++17 -ffp-contract=off
@@ -28,7 +28,11 @@
 namespace {
 
 struct P3 { float x, y, z; };
+#if defined(ORC_REDUX3_LEFT)                                   // sensitivity-sweep variant, see registration_oracle.cpp
+static inline float red3(float a0, float a1, float a2) { return (a0 + a1) + a2; }
+#else
 static inline float red3(float a0, float a1, float a2) { return a0 + (a1 + a2); }
+#endif
 static inline float sqnorm(const P3& a, const P3& b) {   // (a - b).squaredNorm()
     float d0 = a.x - b.x, d1 = a.y - b.y, d2 = a.z - b.z;
     return red3(d0 * d0, d1 * d1, d2 * d2);

@@ -45,7 +45,14 @@ struct M3 { float a[3][3]; };   // a[row][col]
 
 // Eigen's fully unrolled, non-vectorised redux of 3 coefficients splits the
 // range in halves: redux(0,3) = f(redux(0,1), redux(1,2)) = a0 + (a1 + a2).
+// Variant builds for the sensitivity sweep of oracle/sensitivity.py (Makefile target `variants`): each ORC_* macro swaps
+// ONE of the evaluation orders this restatement assumes of Eigen 3.4 for the other plausible
+// reading, so the sweep can report how many bit-exact outputs depend on it.
+#if defined(ORC_REDUX3_LEFT)
+static inline float red3(float a0, float a1, float a2) { return (a0 + a1) + a2; }                  // left-to-right redux
+#else
 static inline float red3(float a0, float a1, float a2) { return a0 + (a1 + a2); }
+#endif
 
 static inline V3 load3(const float* p) { return V3{{p[0], p[1], p[2]}}; }
 
@@ -202,6 +209,11 @@ static inline M3 rotation_from_svd(const M3& H) {
 // (registration.cpp:366).  In-place, diagonal pivoting, pseudo-inverse of D.
 // ---------------------------------------------------------------------------
 static inline float redn_halving(const float* c, int n) {     // redux_novec_unroller
+#if defined(ORC_LDLT_LINEAR)
+    float acc = c[0];                                          // variant: plain left-to-right sum
+    for (int i = 1; i < n; ++i) acc = acc + c[i];
+    return acc;
+#endif
     if (n == 1) return c[0];
     int h = n / 2;
     return redn_halving(c, h) + redn_halving(c + h, n - h);
@@ -268,10 +280,14 @@ static void ldlt6_solve(const float Ain[6][6], const float bin[6], float x[6]) {
         float c[6];
         for (int j = 0; j < li; ++j) c[j] = m[st + j][di] * d[st + j];
         float sum;
+#if defined(ORC_LDLT_LINEAR)
+        sum = redn_halving(c, li);
+#else
         if (li >= 4) {
             sum = (c[0] + c[2]) + (c[1] + c[3]);            // SSE predux: (a0+a2)+(a1+a3)
             if (li == 5) sum = sum + c[4];
         } else sum = redn_halving(c, li);
+#endif
         d[di] -= sum;
     }
     // P^T
@@ -294,12 +310,24 @@ static inline Quat quat_from_aa(float angle, int axis) {
     q.x = v[0]; q.y = v[1]; q.z = v[2];
     return q;
 }
+// Quaternionf * Quaternionf.  On x86-64 (SSE2 is baseline, EIGEN_VECTORIZE_SSE is on by default) Eigen 3.4 does not
+// run the generic scalar product but internal::quat_product<Architecture::Target, ..., float> (Geometry/arch/
+// Geometry_SIMD.h): with a = (x,y,z,w) packets, res = (a * b.wwww - a.zxyx * b.yzxx) + (sign-flipped in w)(a.yzxz * b.zxyz
+// + a.wwwy * b.xyzy), i.e. per coefficient (t1 - t2) + (s1 + s2), the w lane negating its second parenthesis.
+// ORC_QUAT_SCALAR: the generic template's left-to-right order instead (round 1's reading; moves ICP results at 1e-7).
 static inline Quat quat_mul(const Quat& a, const Quat& b) {
     Quat r;
+#if defined(ORC_QUAT_SCALAR)
     r.w = a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z;
     r.x = a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y;
     r.y = a.w * b.y + a.y * b.w + a.z * b.x - a.x * b.z;
     r.z = a.w * b.z + a.z * b.w + a.x * b.y - a.y * b.x;
+#else
+    r.x = (a.x * b.w - a.z * b.y) + (a.y * b.z + a.w * b.x);
+    r.y = (a.y * b.w - a.x * b.z) + (a.z * b.x + a.w * b.y);
+    r.z = (a.z * b.w - a.y * b.x) + (a.x * b.y + a.w * b.z);
+    r.w = (a.w * b.w - a.x * b.x) + (-(a.z * b.z + a.y * b.y));
+#endif
     return r;
 }
 static inline M3 quat_to_matrix(const Quat& q) {
@@ -323,8 +351,12 @@ static inline void T_mul(const float* A, const float* B, float* C) {
     float out[16];
     for (int j = 0; j < 4; ++j)
         for (int i = 0; i < 4; ++i) {
+#if defined(ORC_MAT4_PAIRWISE)
+            float r = (T_at(A, i, 0) * T_at(B, 0, j) + T_at(A, i, 1) * T_at(B, 1, j)) + (T_at(A, i, 2) * T_at(B, 2, j) + T_at(A, i, 3) * T_at(B, 3, j));
+#else
             float r = T_at(A, i, 0) * T_at(B, 0, j);
             for (int k = 1; k < 4; ++k) r = T_at(A, i, k) * T_at(B, k, j) + r;
+#endif
             out[j * 4 + i] = r;
         }
     std::memcpy(C, out, sizeof(out));

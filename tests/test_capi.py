@@ -81,19 +81,3 @@ def test_point_cloud_mirror_semantics(b3d):
     r = b3d.RegistrationResult()
     assert np.array_equal(r.transformation, np.eye(4)) and r.fitness == 0.0 and r.rmse == 0.0
     assert b3d.FPFHFeatures(np.zeros((7, 33), np.float32)).size() == 7
-
-
-def test_filter_duplicates_follows_the_reference_rule():
-    """pipeline.cpp:153-180: first-come slots, replace by the pose nearer the origin, compare only against kept poses."""
-    import importlib
-    pipe = importlib.import_module("3dvision_b200.pipeline")
-
-    def pose(x, y, z):
-        T = np.eye(4, dtype=np.float32); T[:3, 3] = (x, y, z); return T
-    wps = [pose(1, 0, 0), pose(1.01, 0, 0), pose(0.99, 0, 0), pose(2, 0, 0), pose(0.985, 0, 0)]
-    out = pipe.filter_duplicates(wps, 0.02)
-    assert len(out) == 2
-    assert np.allclose(out[0][:3, 3], (0.985, 0, 0)) and np.allclose(out[1][:3, 3], (2, 0, 0))
-    assert pipe.filter_duplicates([], 0.1) == []
-    T = pose(0.1, -0.2, 0.3)
-    assert np.allclose(pipe.world_pose(T) @ T, np.eye(4), atol=1e-6)

@@ -63,4 +63,41 @@ def test_shim_matches_oracle_through_cpp(tmp_path, oracle):
     refi = oracle.icp(c.source, c.target, c.target_normals, ref.transformation, icp_thr, icp_iter, True)
     assert res[1, 16] == np.float32(refi.fitness)
     assert syn.rotation_error(T[1], refi.transformation) < 1e-5 and syn.translation_error(T[1], refi.transformation) < 1e-6
+    assert np.array_equal(T[1], refi.transformation) and res[1, 17] == np.float32(refi.rmse)      # the shim runs the reference-order mode
     assert np.array_equal(res[1], res[2])             # GPURegistration::icpRefine == icpRefine(point_to_plane = true)
+
+
+@pytest.mark.gpu
+def test_shim_worker_pool_spreads_over_the_gpus_with_identical_results(tmp_path, oracle, b3d):
+    """The orchestrator's pool threads (pipeline.cpp:321-327) each get their own context, dealt round-robin over the usable
+    GPUs (one on a 1-GPU box; run under `gpurun --gpus 2` to see both).  Every thread must return the single-GPU result bit
+    for bit, and the pose post-processing (pipeline.cpp:136-137, 153-180) must equal the oracle's."""
+    exe = build_driver(tmp_path, False)
+    c = syn.ransac_case(n_src=1800, n_tgt=1500, seed=77, max_iterations=1500)
+    icp_thr, icp_iter, nt = 0.004, 15, 6
+    inp, out = tmp_path / "in.bin", tmp_path / "pool.bin"
+    with open(inp, "wb") as f:
+        f.write(struct.pack("<4I3f", c.source.shape[0], c.target.shape[0], c.max_iterations, icp_iter, c.voxel_size, 0.999, icp_thr))
+        for a in (c.source, c.target, c.target_normals, c.source_desc, c.target_desc):
+            f.write(np.ascontiguousarray(a, np.float32).tobytes())
+    subprocess.run([exe, "pool", str(inp), str(out), str(nt)], check=True)
+    raw = np.fromfile(out, np.uint8)
+    rec = 4 + 3 * 18 * 4 + 64
+    devices, first = [], None
+    ref = oracle.ransac_registration(c.source, c.target, c.source_desc, c.target_desc, c.voxel_size, c.max_iterations, 0.999)
+    refi = oracle.icp(c.source, c.target, c.target_normals, ref.transformation, icp_thr, icp_iter, True)
+    ext = np.eye(4, dtype=np.float32); ext[:3, 3] = (0.5, -0.25, 1.0)
+    for t in range(nt):
+        blob = raw[t * rec:(t + 1) * rec]
+        devices.append(int(blob[:4].view(np.int32)[0]))
+        body = blob[4:].view(np.float32)
+        first = body if first is None else first
+        assert np.array_equal(body, first)                                         # every worker, whichever GPU: same bits
+    res = first[:54].reshape(3, 18)
+    assert np.array_equal(res[0, :16].reshape(4, 4).T, ref.transformation) and np.array_equal(res[1, :16].reshape(4, 4).T, refi.transformation)
+    assert np.array_equal(first[54:70].reshape(4, 4).T, oracle.world_pose(refi.transformation, ext))
+    n_dev = b3d._capi.lib().b3d_device_count()
+    assert sorted(set(devices)) == list(range(min(n_dev, nt)))                     # dealt round-robin over every usable GPU
+    tail = raw[nt * rec:]
+    kept = int(tail[:4].view(np.uint32)[0])
+    assert kept == 1 and np.array_equal(tail[4:68].view(np.float32), first[54:70])  # six identical waypoints collapse to one

@@ -272,3 +272,50 @@ def test_register_depth_equals_deprojection_then_register_scene(b3d):
         assert a["refined"][1:] == b["refined"][1:]
     finally:
         c2.close()
+
+
+# ------------------------------------------------------------------ rest of row f-4: mask resize, world pose, duplicate filter
+@pytest.mark.parametrize("mh,mw", [(60, 80), (181, 321), (360, 640), (7, 5)])
+def test_depth_to_cloud_resizes_the_mask_like_the_reference(ctx, oracle, mh, mw):
+    """A mask smaller / larger than the depth image goes through cv::resize(..., INTER_NEAREST) first (pipeline.cpp:39-41);
+    the device reads the mask through the same source-pixel map instead of materialising the resized image."""
+    rng = np.random.default_rng(mh * 1000 + mw)
+    h, w = 180, 320
+    depth = rng.integers(300, 1400, (h, w)).astype(np.uint16)
+    mask = (rng.random((mh, mw)) < 0.6).astype(np.uint8) * 255
+    args = (1000.0, 1.5, 300.0, 310.0, w / 2.0, h / 2.0)
+    want, _ = oracle.depth_to_cloud(depth, oracle.resize_mask_nearest(mask, w, h), *args)
+    got, _ = ctx.depth_to_cloud(depth, mask, *args)
+    assert got.shape[0] > 1000 and np.array_equal(got, want)
+
+
+def test_world_poses_bit_identical(ctx, oracle):
+    """pipeline.cpp:136-137 on the device == the oracle's restatement of Eigen's SSE inverse + packet product."""
+    rng = np.random.default_rng(9)
+    Ts = np.stack([syn.rigid(rng.standard_normal(3), float(rng.uniform(-170, 170)), rng.uniform(-1, 1, 3)).astype(np.float32) for _ in range(70)])
+    Ts[5] = rng.standard_normal((4, 4)).astype(np.float32)                        # not rigid: the general 4x4 path
+    ext = syn.rigid([0.1, 0.2, 0.9], 33.0, [0.4, -0.2, 1.1]).astype(np.float32)
+    got = ctx.world_poses(Ts, ext)
+    for T, g in zip(Ts, got):
+        assert np.array_equal(g, oracle.world_pose(T, ext))
+    got = ctx.world_poses(Ts)
+    for T, g in zip(Ts, got):
+        assert np.array_equal(g, oracle.world_pose(T))
+    assert ctx.world_poses(np.zeros((0, 4, 4), np.float32)).shape == (0, 4, 4)
+
+
+def test_filter_duplicates_bit_identical(ctx, oracle, b3d):
+    rng = np.random.default_rng(10)
+    centres = rng.uniform(-0.5, 0.5, (12, 3))
+    wps = []
+    for i in range(64):                                                           # clusters of near-duplicate detections
+        T = np.eye(4, dtype=np.float32); T[:3, 3] = centres[rng.integers(0, 12)] + rng.normal(0, 0.004, 3)
+        wps.append(T)
+    for min_d in (0.0, 0.005, 0.02, 0.3, 10.0):
+        want = oracle.filter_duplicates(wps, min_d)
+        got = ctx.filter_duplicates(wps, min_d)
+        assert len(got) == len(want) and all(np.array_equal(a, b) for a, b in zip(got, want)), min_d
+    assert ctx.filter_duplicates([], 0.1) == []
+    pipe = importlib.import_module("3dvision_b200.pipeline")                      # the orchestrator mirror goes through the same entry
+    assert all(np.array_equal(a, b) for a, b in zip(pipe.filter_duplicates(wps, 0.02), oracle.filter_duplicates(wps, 0.02)))
+    assert np.array_equal(pipe.world_pose(wps[3]), oracle.world_pose(wps[3]))

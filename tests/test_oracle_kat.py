@@ -266,3 +266,51 @@ def test_depth_to_cloud_oracle_reproduces_the_demo_scene_and_known_pixels(oracle
     assert np.allclose(rgb, np.array([[2, 1, 0]], np.float32) / 255.0, atol=0, rtol=0)
     xyz2, _ = oracle.depth_to_cloud(d, m, 1000.0, 1.6, 2.0, 4.0, 1.0, 0.5)           # a looser clip keeps the 1.5000001 m and 1.501 m pixels
     assert xyz2.shape[0] == 3 and xyz2[1, 2] == np.float32(1500) * a and xyz2[2, 2] == np.float32(1501) * a
+
+
+# ------------------------------------------------------------------ pose post-processing, mask resize (pipeline.cpp:38-41, 136-137, 153-180)
+def _pose(x, y, z):
+    T = np.eye(4, dtype=np.float32); T[:3, 3] = (x, y, z); return T
+
+
+def test_filter_duplicates_oracle_follows_the_reference_rule(oracle):
+    """pipeline.cpp:153-180: first-come slots, replace by the pose nearer the origin, compare only against kept poses."""
+    wps = [_pose(1, 0, 0), _pose(1.01, 0, 0), _pose(0.99, 0, 0), _pose(2, 0, 0), _pose(0.985, 0, 0)]
+    out = oracle.filter_duplicates(wps, 0.02)
+    assert len(out) == 2
+    assert np.array_equal(out[0], wps[4]) and np.array_equal(out[1], wps[3])      # 0.985 replaced the slot of the first pose
+    assert oracle.filter_duplicates([], 0.1) == []
+    # strict '<': a pose exactly min_distance away is NOT a duplicate; an equally distant duplicate does not replace
+    out = oracle.filter_duplicates([_pose(1, 0, 0), _pose(1.5, 0, 0), _pose(-1, 0, 0)], 0.5)
+    assert len(out) == 3
+    out = oracle.filter_duplicates([_pose(1, 0, 0), _pose(0, 1, 0)], 2.0)
+    assert len(out) == 1 and np.array_equal(out[0], _pose(1, 0, 0))
+
+
+def test_mat4_inverse_oracle_is_an_inverse_and_exact_on_easy_cases(oracle):
+    """Eigen's SSE 4x4 inverse restated (2x2-block cofactors).  It must (a) invert, (b) be exact where every product is."""
+    rng = np.random.default_rng(0)
+    for _ in range(100):
+        M = rng.standard_normal((4, 4)).astype(np.float32)
+        ref = np.linalg.inv(M.astype(np.float64))
+        assert np.abs(oracle.mat4_inverse(M) - ref).max() <= 2e-4 * max(1.0, np.abs(ref).max() ** 2)
+    assert np.array_equal(oracle.mat4_inverse(np.eye(4, dtype=np.float32)), np.eye(4, dtype=np.float32))
+    D = np.diag(np.float32([2, 4, 0.5, 8]))
+    assert np.array_equal(oracle.mat4_inverse(D), np.diag(np.float32([0.5, 0.25, 2, 0.125])))
+    P = np.eye(4, dtype=np.float32)[[2, 0, 3, 1]]                                    # a permutation: inverse = transpose, exactly
+    assert np.array_equal(oracle.mat4_inverse(P), P.T)
+    T = _pose(0.25, -0.5, 2.0); T[:3, :3] = np.float32([[0, -1, 0], [1, 0, 0], [0, 0, 1]])
+    Ti = oracle.mat4_inverse(T)
+    assert np.array_equal(Ti @ T, np.eye(4, dtype=np.float32))
+    ext = _pose(0.5, 0.25, -1.0)
+    assert np.array_equal(oracle.world_pose(T, ext), (ext @ Ti).astype(np.float32)) and np.array_equal(oracle.world_pose(T), Ti)
+
+
+def test_mask_resize_oracle_equals_opencv(oracle):
+    """cv::resize(..., INTER_NEAREST) restated; OpenCV's Python module is present in this image, so this one IS pinned
+    against the third-party implementation the reference calls (pipeline.cpp:40)."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(1)
+    for sh, sw, dh, dw in ((240, 320, 720, 1280), (721, 1283, 720, 1280), (100, 100, 37, 53), (5, 7, 480, 640), (720, 1280, 720, 1280), (1, 1, 9, 4)):
+        m = rng.integers(0, 256, (sh, sw)).astype(np.uint8)
+        assert np.array_equal(oracle.resize_mask_nearest(m, dw, dh), cv2.resize(m, (dw, dh), interpolation=cv2.INTER_NEAREST)), (sh, sw, dh, dw)
