@@ -25,11 +25,12 @@ NO_MATCH = 0xFFFFFFFF
 
 # every symbol include/b3d.h declares (tests check the library exports exactly these)
 SYMBOLS = [
-    "b3d_device_count",
+    "b3d_device_count", "b3d_comm_unique_id", "b3d_comm_init", "b3d_comm_attach", "b3d_comm_destroy",
+    "b3d_ransac_sharded", "b3d_ransac_sharded_resident", "b3d_register_scene_sharded",
     "b3d_cuda_available", "b3d_ctx_create", "b3d_ctx_destroy", "b3d_ctx_set_stream", "b3d_strerror", "b3d_last_error",
     "b3d_ransac", "b3d_icp",
     "b3d_set_clouds", "b3d_set_features", "b3d_set_match_mode", "b3d_match_features", "b3d_get_correspondences", "b3d_get_correspondences_dev", "b3d_set_correspondences",
-    "b3d_correspondences_devptr", "b3d_set_score_mode", "b3d_ransac_prepare", "b3d_ransac_score", "b3d_ransac_reduce", "b3d_ransac_finish",
+    "b3d_correspondences_devptr", "b3d_set_score_mode", "b3d_ransac_prepare", "b3d_ransac_score", "b3d_ransac_reduce", "b3d_ransac_reduce3", "b3d_ransac_finish", "b3d_set_finish_mode",
     "b3d_ransac_counts", "b3d_ransac_hypotheses", "b3d_set_icp_mode", "b3d_icp_run", "b3d_icp_nearest",
     "b3d_kernel_launches", "b3d_stage_ms", "b3d_measure_fp32_rate", "b3d_score_recounts", "b3d_icp_exact_sum_stats",
     "b3d_prepare_model", "b3d_register_scene", "b3d_register_scene_device", "b3d_depth_to_cloud", "b3d_register_depth", "b3d_world_poses", "b3d_filter_duplicates", "b3d_voxel_downsample", "b3d_set_voxel_order_mode", "b3d_estimate_normals", "b3d_compute_fpfh",
@@ -66,6 +67,8 @@ def lib():
 
 
 _vp = C.c_void_p
+_fp = C.POINTER(C.c_float)
+_ip = C.POINTER(C.c_int32)
 _f32p = C.POINTER(C.c_float)
 _i32p = C.POINTER(C.c_int32)
 
@@ -97,6 +100,8 @@ def _declare(L):
     L.b3d_ransac_prepare.argtypes = [_vp, C.c_float, C.c_int, C.c_float]
     L.b3d_ransac_score.argtypes = [_vp, C.c_int, C.c_int]
     L.b3d_ransac_reduce.argtypes = [_vp, C.c_int, C.c_int, _vp, _vp]
+    L.b3d_ransac_reduce3.argtypes = [_vp, C.c_int, C.c_int, _vp]
+    L.b3d_set_finish_mode.argtypes = [_vp, C.c_int]
     L.b3d_ransac_finish.argtypes = [_vp, _vp, _f32p, _f32p, _f32p, _i32p]
     L.b3d_ransac_counts.argtypes = [_vp, C.c_int, C.c_int, _vp]
     L.b3d_ransac_hypotheses.argtypes = [_vp, C.c_int, C.c_int, _vp]
@@ -116,6 +121,14 @@ def _declare(L):
     L.b3d_register_depth.argtypes = [_vp, _vp, C.c_int, C.c_int, _vp, C.c_int, C.c_int] + [C.c_float] * 6 + [C.c_float, C.c_int, C.c_float, C.c_int,
                                      C.c_float, C.c_float, C.c_int, C.c_int, C.POINTER(SceneResult)]
     L.b3d_world_poses.argtypes = [_vp, _vp, C.c_size_t, _vp, _vp]
+    L.b3d_comm_unique_id.argtypes = [_vp]
+    L.b3d_comm_init.argtypes = [_vp, _vp, C.c_int, C.c_int]
+    L.b3d_comm_attach.argtypes = [_vp, _vp, C.c_int, C.c_int]
+    L.b3d_comm_destroy.argtypes = [_vp]
+    L.b3d_ransac_sharded.argtypes = [_vp, _vp, C.c_size_t, _vp, C.c_size_t, _vp, _vp, C.c_float, C.c_int, C.c_float, _vp, _fp, _fp, _ip]
+    L.b3d_ransac_sharded_resident.argtypes = [_vp, C.c_float, C.c_int, C.c_float, C.c_int, _vp, _fp, _fp, _ip]
+    L.b3d_register_scene_sharded.argtypes = [_vp, _vp, C.c_size_t, C.c_float, C.c_int, C.c_float, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int,
+                                             C.POINTER(SceneResult)]
     L.b3d_filter_duplicates.argtypes = [_vp, _vp, C.c_size_t, C.c_float, _vp, C.POINTER(C.c_size_t)]
     L.b3d_register_scene_device.argtypes = [_vp, _vp, C.c_size_t, C.c_float, C.c_int, C.c_float, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int,
                                             C.POINTER(SceneResult)]
@@ -226,6 +239,54 @@ class Context:
                                        T.ctypes.data_as(_f32p), C.byref(fit), C.byref(rm), C.byref(best)))
         return _T_from_colmajor(T), fit.value, rm.value, best.value
 
+    # ---- multi-GPU (include/b3d.h "multi-GPU"): this context as one rank of an NCCL group -------------------------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        rc = lib().b3d_comm_unique_id(buf)
+        if rc != B3D_OK:
+            raise B3DError(rc, lib().b3d_strerror(rc).decode())
+        return buf.raw
+
+    def comm_init(self, unique_id: bytes | None, rank: int, world: int):
+        """ncclCommInitRank on this context's device (collective); world == 1 needs no id."""
+        self._check(self._L.b3d_comm_init(self._h, C.c_char_p(unique_id) if unique_id is not None else None, int(rank), int(world)))
+        self.rank, self.world = int(rank), int(world)
+
+    def comm_destroy(self):
+        self._check(self._L.b3d_comm_destroy(self._h))
+        self.rank, self.world = 0, 1
+
+    def ransac_sharded(self, src, tgt, src_desc, tgt_desc, voxel_size, max_iterations=100000, confidence=0.999):
+        """b3d_ransac_sharded: collective; host buffers in, each rank uploads only its rows of the source descriptors."""
+        src = _as_f32(src, 3); tgt = _as_f32(tgt, 3); sd = _as_f32(src_desc, 33); td = _as_f32(tgt_desc, 33)
+        T = np.empty(16, np.float32); fit = C.c_float(); rm = C.c_float(); best = C.c_int32()
+        self._n_src, self._n_tgt, self._H = src.shape[0], tgt.shape[0], max_iterations
+        self._check(self._L.b3d_ransac_sharded(self._h, _ptr(src), src.shape[0], _ptr(tgt), tgt.shape[0], _ptr(sd), _ptr(td), voxel_size,
+                                               max_iterations, confidence, _ptr(T), C.byref(fit), C.byref(rm), C.byref(best)))
+        return _T_from_colmajor(T), fit.value, rm.value, best.value
+
+    def ransac_sharded_resident(self, voxel_size, max_iterations=100000, confidence=0.999, match=True):
+        T = np.empty(16, np.float32); fit = C.c_float(); rm = C.c_float(); best = C.c_int32()
+        self._H = max_iterations
+        self._check(self._L.b3d_ransac_sharded_resident(self._h, voxel_size, max_iterations, confidence, int(bool(match)), _ptr(T),
+                                                        C.byref(fit), C.byref(rm), C.byref(best)))
+        return _T_from_colmajor(T), fit.value, rm.value, best.value
+
+    def register_scene_sharded(self, scene_xyz, voxel_size, normals_k=30, fpfh_radius=None, ransac_max_iterations=100000, confidence=0.999,
+                               icp_threshold=None, icp_max_iterations=200, point_to_plane=True):
+        xyz = _as_f32(scene_xyz, 3)
+        radius = voxel_size * 5.0 if fpfh_radius is None else fpfh_radius
+        thr = voxel_size * 0.4 if icp_threshold is None else icp_threshold
+        r = SceneResult()
+        self._check(self._L.b3d_register_scene_sharded(self._h, _ptr(xyz), xyz.shape[0], voxel_size, int(normals_k), radius,
+                                                       int(ransac_max_iterations), confidence, thr, int(icp_max_iterations),
+                                                       int(bool(point_to_plane)), C.byref(r)))
+        self._n_src = r.n_source_points; self._H = int(ransac_max_iterations)
+        return {"coarse": (_T_from_colmajor(np.array(r.coarse_T, np.float32)), r.coarse_fitness, r.coarse_rmse, r.coarse_best_iteration),
+                "refined": (_T_from_colmajor(np.array(r.T, np.float32)), r.fitness, r.rmse, r.icp_iterations),
+                "n_source_points": int(r.n_source_points)}
+
     def icp(self, src, tgt, tgt_normals, T0, distance_threshold, max_iterations=200, point_to_plane=True):
         src = _as_f32(src, 3); tgt = _as_f32(tgt, 3)
         nrm = _as_f32(tgt_normals, 3) if tgt_normals is not None else None
@@ -307,6 +368,13 @@ class Context:
 
     def ransac_reduce(self, h0, h1, keys_devptr: int, limit_devptr: int | None = None):
         self._check(self._L.b3d_ransac_reduce(self._h, h0, h1, _vp(limit_devptr) if limit_devptr else None, _vp(keys_devptr)))
+
+    def set_finish_mode(self, mode: int):
+        """RANSAC rmse sum: 0 parallel exact (default), 1 one-chain kernel; same bits."""
+        self._check(self._L.b3d_set_finish_mode(self._h, int(mode)))
+
+    def ransac_reduce3(self, h0, h1, keys3_devptr: int):
+        self._check(self._L.b3d_ransac_reduce3(self._h, h0, h1, _vp(keys3_devptr)))
 
     def ransac_finish(self, keys_devptr: int):
         T = np.empty(16, np.float32); fit = C.c_float(); rm = C.c_float(); best = C.c_int32()

@@ -134,11 +134,12 @@ void b3d_ctx_destroy(b3d_ctx* c) {
     alloc_stream_valid() = false;
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->own_stream && c->own_stream != c->stream) cudaStreamSynchronize(c->own_stream);
+    comm_destroy_impl(c);
     DevBuf* bufs[] = {&c->stage_a, &c->stage_b, &c->stage_c, &c->src4, &c->tgt4, &c->nrm4, &c->sdesc, &c->tdesc, &c->corr, &c->raw,
                       &c->draws, &c->scan_tmp, &c->hyp, &c->counts, &c->pairs, &c->seqsum, &c->grid_slots, &c->grid_cursor,
                       &c->grid_pts, &c->grid_nrm, &c->pt_slot, &c->pt_rank, &c->partials, &c->nn_idx, &c->nn_d2, &c->state,
                       &c->seq_rec, &c->seq_match, &c->seq_P, &c->seq_Q, &c->seq_N, &c->ess_terms, &c->ess_bsum, &c->ess_guess, &c->ess_summ, &c->fine_slots, &c->fine_pts, &c->nbh_slot27, &c->nbh_cursor, &c->icp_cache, &c->icp_cache_idx, &c->bail_list_a, &c->bail_list_b, &c->bail_state, &c->src_slots, &c->src_sorted, &c->src_slot, &c->src_rank,
-                      &c->tc_a_tiles, &c->tc_b_tiles, &c->tc_norm2, &c->tc_best, &c->tc_aux};
+                      &c->tc_a_tiles, &c->tc_b_tiles, &c->tc_norm2, &c->tc_best, &c->tc_aux, &c->dist_keys};
     for (DevBuf* b : bufs) b->release();
     for (DevBuf& b : c->fbuf) b.release();
     if (c->h_state) cudaFreeHost(c->h_state);
@@ -338,6 +339,12 @@ int b3d_set_icp_mode(b3d_ctx* c, int mode) {
     return B3D_OK;
 }
 
+int b3d_set_finish_mode(b3d_ctx* c, int mode) {
+    if (!c || mode < 0 || mode > 1) return B3D_ERR_INVALID;
+    c->finish_mode = mode;
+    return B3D_OK;
+}
+
 int b3d_set_score_mode(b3d_ctx* c, int mode) {
     if (!c || mode < 0 || mode > 4) return B3D_ERR_INVALID;
     c->score_mode = mode;
@@ -404,6 +411,12 @@ int b3d_ransac_reduce(b3d_ctx* c, int h0, int h1, const int64_t* limit_key_dev, 
     B3D_CUDA(c, enter(c));
     return ransac_reduce_impl(c, h0, h1, limit_key_dev, keys_dev);
 }
+int b3d_ransac_reduce3(b3d_ctx* c, int h0, int h1, int64_t* keys3_dev) {
+    if (!c) return B3D_ERR_INVALID;
+    B3D_CUDA(c, enter(c));
+    return ransac_reduce3_impl(c, h0, h1, reinterpret_cast<unsigned long long*>(keys3_dev));
+}
+
 int b3d_ransac_finish(b3d_ctx* c, const int64_t* keys_dev, float* T, float* fitness, float* rmse, int32_t* best) {
     if (!c || !T || !fitness || !rmse) return B3D_ERR_INVALID;
     B3D_CUDA(c, enter(c));

@@ -66,6 +66,8 @@ struct DeviceState {
     float ess_means[8];               // point-to-point: src_mean(3), tgt_mean(3) between the two passes
     unsigned int ess_stats[32][4];    // per sum, accumulated over the call: walk rounds, blocks added term by term, SM cycles / 16 (diagnostic)
     float out18[20];                  // RANSAC result: T(16), fitness, rmse, best id (as int bits), unused
+    float fin_Rt[12];                 // RANSAC finish: the winner's (R row-major, t), rebuilt from its index triple
+    int fin_id, fin_none;             // the winner's id; 1 if no hypothesis had an inlier
 };
 
 }  // namespace b3d
@@ -117,6 +119,9 @@ struct b3d_ctx {
     b3d::DevBuf icp_cache, icp_cache_idx;                    // per query slot: reference position + hold radius^2, and the match it certifies
     b3d::DevBuf seq_rec, seq_match, seq_P, seq_Q, seq_N;            // reference-order sums: per-query records (legacy chain: compacted pairs)
     b3d::DevBuf ess_terms, ess_bsum, ess_guess, ess_summ;           // exact sequential sums (b3d_ess.cuh): terms, fp64 block sums, guesses, summaries
+    bool fin_smem_opt_in = false;
+    int finish_mode = 0;                                     // RANSAC rmse: 0 parallel exact sum (b3d_ess.cuh), 1 one dependent add chain
+    bool ess_smem_opt_in = false;                            // cudaFuncSetAttribute done on this context's device
     int icp_mode = 0;                                        // 0 / 2: sums in the reference's order (exact, parallel); 1: fp64 tree sums; 3: legacy one-chain replay
     b3d::DevBuf src_slots, src_sorted, src_slot, src_rank;   // source reordered by target cell (coherent warps)
 
@@ -125,6 +130,12 @@ struct b3d_ctx {
     b3d::DevBuf fbuf[kFeatureBufs];
     bool model_ready = false;                // b3d_prepare_model has left the target cloud / normals / FPFH resident
     int voxel_order_mode = 0;                // 0: container order simulated on the device; 1: real std::unordered_map on the host
+
+    // multi-GPU (b3d_dist.cu): communicator of the group this context is a rank of
+    void* comm = nullptr;                    // ncclComm_t
+    bool comm_owned = false;                 // created by b3d_comm_init (else attached)
+    int comm_rank = 0, comm_world = 1;
+    b3d::DevBuf dist_keys;                   // u64 [world + 1][3]: the gathered selection keys
 
     // device scalars + pinned host mirror
     b3d::DevBuf state;                       // b3d::DeviceState
@@ -180,6 +191,11 @@ int ransac_generate_impl(b3d_ctx* c, int h0, int h1);
 int ransac_score_impl(b3d_ctx* c, int h0, int h1);
 int ransac_reduce_impl(b3d_ctx* c, int h0, int h1, const int64_t* limit_key_dev, int64_t* keys_dev);
 int ransac_finish_impl(b3d_ctx* c, const int64_t* keys_dev, float* T, float* fitness, float* rmse, int32_t* best);
+int ransac_reduce3_impl(b3d_ctx* c, int h0, int h1, unsigned long long* keys3_dev);
+int comm_destroy_impl(b3d_ctx* c);
+int ransac_sharded_resident_impl(b3d_ctx* c, float voxel, int H, float confidence, int match, float* T, float* fitness, float* rmse, int32_t* best);
+int register_scene_sharded_impl(b3d_ctx* c, const float* xyz, size_t n, float voxel, int k, float radius, int ransac_iterations, float confidence,
+                                float icp_threshold, int icp_iterations, int point_to_plane, b3d_scene_result* out);
 int icp_run_impl(b3d_ctx* c, const float* T0, float thr, int max_iter, int p2plane, int stop_on_conv,
                  float* T, float* fitness, float* rmse, int32_t* iters);
 int icp_nearest_impl(b3d_ctx* c, const float* T, float thr, uint32_t* idx_host, float* d2_host);

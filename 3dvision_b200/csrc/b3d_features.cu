@@ -964,16 +964,21 @@ int prepare_model_impl(b3d_ctx* c, const float* xyz, size_t n, float voxel, int 
 }
 
 static int register_resident(b3d_ctx* c, const float* xyz, bool on_device, size_t n, float voxel, int k, float radius, int ransac_iterations,
-                             float confidence, float icp_threshold, int icp_iterations, int point_to_plane, b3d_scene_result* out);
+                             float confidence, float icp_threshold, int icp_iterations, int point_to_plane, b3d_scene_result* out, bool sharded);
 
 int register_scene_impl(b3d_ctx* c, const float* xyz, size_t n, float voxel, int k, float radius, int ransac_iterations, float confidence,
                         float icp_threshold, int icp_iterations, int point_to_plane, b3d_scene_result* out) {
-    return register_resident(c, xyz, false, n, voxel, k, radius, ransac_iterations, confidence, icp_threshold, icp_iterations, point_to_plane, out);
+    return register_resident(c, xyz, false, n, voxel, k, radius, ransac_iterations, confidence, icp_threshold, icp_iterations, point_to_plane, out, false);
+}
+
+int register_scene_sharded_impl(b3d_ctx* c, const float* xyz, size_t n, float voxel, int k, float radius, int ransac_iterations, float confidence,
+                                float icp_threshold, int icp_iterations, int point_to_plane, b3d_scene_result* out) {
+    return register_resident(c, xyz, false, n, voxel, k, radius, ransac_iterations, confidence, icp_threshold, icp_iterations, point_to_plane, out, true);
 }
 
 int register_scene_device_impl(b3d_ctx* c, const float* xyz_dev, size_t n, float voxel, int k, float radius, int ransac_iterations, float confidence,
                                float icp_threshold, int icp_iterations, int point_to_plane, b3d_scene_result* out) {
-    return register_resident(c, xyz_dev, true, n, voxel, k, radius, ransac_iterations, confidence, icp_threshold, icp_iterations, point_to_plane, out);
+    return register_resident(c, xyz_dev, true, n, voxel, k, radius, ransac_iterations, confidence, icp_threshold, icp_iterations, point_to_plane, out, false);
 }
 
 // depth image + mask of one instance -> pose: Pipeline::processInstance (pipeline.cpp:38-129) up to the refined transform
@@ -987,11 +992,11 @@ int register_depth_impl(b3d_ctx* c, const uint16_t* depth, int w, int h, const u
     int rc = depth_to_cloud_dev(c, depth, w, h, mask, mask_w, mask_h, scale, clip, fx, fy, cx, cy, nullptr, &n);
     if (rc != B3D_OK) return rc;
     return register_resident(c, c->fbuf[F_IMG_XYZ].as<float>(), true, n, voxel, k, radius, ransac_iterations, confidence, icp_threshold,
-                             icp_iterations, point_to_plane, out);
+                             icp_iterations, point_to_plane, out, false);
 }
 
 static int register_resident(b3d_ctx* c, const float* xyz, bool on_device, size_t n, float voxel, int k, float radius, int ransac_iterations,
-                             float confidence, float icp_threshold, int icp_iterations, int point_to_plane, b3d_scene_result* out) {
+                             float confidence, float icp_threshold, int icp_iterations, int point_to_plane, b3d_scene_result* out, bool sharded) {
     if (!c->model_ready) return fail(c, B3D_ERR_STATE, "register_scene: call b3d_prepare_model first");
     if (n > 0x7FFFFFFFu) return fail(c, B3D_ERR_INVALID, "register_scene: too many points");
     for (int i = 0; i < 16; ++i) out->coarse_T[i] = out->T[i] = (i % 5 == 0) ? 1.0f : 0.0f;    // RegistrationResult defaults (registration.hpp:27-29)
@@ -1003,6 +1008,15 @@ static int register_resident(b3d_ctx* c, const float* xyz, bool on_device, size_
     out->n_source_points = m;
     c->n_src = m; c->sdesc_p = c->sdesc.as<float>();
     c->have_clouds = true; c->have_feats = true;
+    if (sharded) {
+        // every rank ran the (cheap, deterministic) front end on the whole scene; matching rows and hypothesis ids are split
+        // over the communicator (b3d_dist.cu); the refinement runs on every rank from the same coarse pose ("single-cloud ICP
+        // stays on one GPU": replicas, no collective)
+        int rcs = ransac_sharded_resident_impl(c, voxel, ransac_iterations, confidence, 1, out->coarse_T, &out->coarse_fitness, &out->coarse_rmse,
+                                               &out->coarse_best_iteration);
+        if (rcs != B3D_OK) return rcs;
+        return b3d_icp_run(c, out->coarse_T, icp_threshold, icp_iterations, point_to_plane, 1, out->T, &out->fitness, &out->rmse, &out->icp_iterations);
+    }
     int rc = b3d_match_features(c, 0, m); if (rc != B3D_OK) return rc;
     rc = b3d_ransac_prepare(c, voxel, ransac_iterations, confidence); if (rc != B3D_OK) return rc;
     rc = b3d_ransac_score(c, 0, ransac_iterations); if (rc != B3D_OK) return rc;

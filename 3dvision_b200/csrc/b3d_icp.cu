@@ -1104,13 +1104,12 @@ int icp_run_impl(b3d_ctx* c, const float* T0, float thr, int max_iter, int p2pla
         B3D_CUDA(c, c->scan_tmp.ensure(sizeof(unsigned) * (seq_tiles + 1)));
     }
     if (exact) {
-        static const cudaError_t smem_opt_in = [] {               // once per process: the chain kernels' TMA ring is larger than 48 KB
-            cudaError_t e = cudaFuncSetAttribute(icp_ess_chain_kernel<kAccPlane, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ess::ChainSmem));
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(icp_ess_chain_kernel<kAccPoint0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ess::ChainSmem));
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(icp_ess_chain_kernel<kAccPoint1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ess::ChainSmem));
-            return e;
-        }();
-        B3D_CUDA(c, smem_opt_in);
+        if (!c->ess_smem_opt_in) {                                // per device: the chain kernels' TMA ring is larger than 48 KB
+            B3D_CUDA(c, cudaFuncSetAttribute(icp_ess_chain_kernel<kAccPlane, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ess::ChainSmem)));
+            B3D_CUDA(c, cudaFuncSetAttribute(icp_ess_chain_kernel<kAccPoint0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ess::ChainSmem)));
+            B3D_CUDA(c, cudaFuncSetAttribute(icp_ess_chain_kernel<kAccPoint1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ess::ChainSmem)));
+            c->ess_smem_opt_in = true;
+        }
         const size_t nv = plane ? kAccPlane : kAccPoint1;
         B3D_CUDA(c, c->ess_terms.ensure(sizeof(float) * nv * ess_stride));
         B3D_CUDA(c, c->ess_bsum.ensure(sizeof(double) * nv * ess_nb_stride));

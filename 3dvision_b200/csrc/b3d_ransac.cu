@@ -20,6 +20,7 @@
 #include "b3d_common.cuh"
 #include "b3d_linalg.cuh"
 #include "b3d_scan.cuh"
+#include "b3d_ess.cuh"
 #include <float.h>
 #include <math.h>
 
@@ -556,8 +557,31 @@ __global__ void bail_prune_kernel(const int* __restrict__ src, const int* __rest
 // ---------------------------------------------------------------------------------
 
 // mode 0: exit key (first id with fitness > confidence).  mode 1: best key over ids <= limit.
+// mode 2: exit key -> out_key[0] AND the best key over all ids of the range -> out_key[1] in one pass (sharded selection).
 __global__ void select_kernel(const int* __restrict__ counts, int h0, int h1, float n_src_f, float confidence,
                               int mode, const long long* __restrict__ limit_key, unsigned long long* __restrict__ out_key) {
+    if (mode == 2) {
+        unsigned long long ex = 0ull, best = 0ull;
+        for (int h = h0 + blockIdx.x * blockDim.x + threadIdx.x; h < h1; h += gridDim.x * blockDim.x) {
+            const int c = counts[h];
+            if (c <= 0) continue;
+            const float fitness = (float)c / n_src_f;
+            const unsigned long long idk = (unsigned long long)(0xFFFFFFFFu - (unsigned)h);
+            if (fitness > confidence) ex = idk > ex ? idk : ex;
+            if (fitness > 0.0f) { const unsigned long long key = ((unsigned long long)__float_as_uint(fitness) << 32) | idk; best = key > best ? key : best; }
+        }
+        ex = warp_max_u64(ex); best = warp_max_u64(best);
+        __shared__ unsigned long long w2[2][32];
+        if ((threadIdx.x & 31) == 0) { w2[0][threadIdx.x >> 5] = ex; w2[1][threadIdx.x >> 5] = best; }
+        __syncthreads();
+        if (threadIdx.x < 64) {
+            const int which = threadIdx.x >> 5, l = threadIdx.x & 31;
+            unsigned long long v = (l < (int)(blockDim.x >> 5)) ? w2[which][l] : 0ull;
+            v = warp_max_u64(v);
+            if (l == 0 && v) atomicMax(out_key + which, v);
+        }
+        return;
+    }
     unsigned limit_id = 0xFFFFFFFFu;
     if (mode == 1 && limit_key) {
         unsigned long long lk = (unsigned long long)(*limit_key);
@@ -710,6 +734,70 @@ finish_kernel(const long long* __restrict__ key_ptr, const uint32_t* __restrict_
         out[15] = 1.0f;
         out[16] = fitness; out[17] = rmse; out[18] = __int_as_float(h);
     }
+}
+
+// ---------------------------------------------------------------------------------
+// winner, parallel form (default): the same reference-order sum of err^2 (registration.cpp:277) through the exact
+// sequential-sum scheme of b3d_ess.cuh — terms (err^2 of the inliers, +0 elsewhere, which leaves an fp32 running sum
+// untouched) -> block summaries -> one warp walks them.  Bit-identical to the one-chain kernel above, which is kept as
+// b3d_set_finish_mode(ctx, 1) for cross-checks.
+// ---------------------------------------------------------------------------------
+__global__ void finish_head_kernel(const long long* __restrict__ key_ptr, const uint32_t* __restrict__ draws, const float4* __restrict__ pairs,
+                                   unsigned pair_stride, DeviceState* __restrict__ st) {
+    if (threadIdx.x != 0) return;
+    const unsigned long long key = (unsigned long long)(*key_ptr);
+    st->seq_count = 0u;
+    if (key == 0ull) { st->fin_none = 1; return; }      // no hypothesis ever beat fitness 0
+    st->fin_none = 0;
+    const int h = (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull));
+    // the winner may have been generated and scored on another rank: rebuild its (R,t) from the index triple
+    float s3[3][3], q3[3][3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const uint32_t id = draws[3 * h + k];
+        const float4 a = pairs[id], b = pairs[pair_stride + id];
+        s3[k][0] = a.x; s3[k][1] = a.y; s3[k][2] = a.z;
+        q3[k][0] = b.x; q3[k][1] = b.y; q3[k][2] = b.z;
+    }
+    Mat3 Rm; float tv[3];
+    kabsch_three_points(s3, q3, Rm, tv);
+    for (int r = 0; r < 3; ++r) { for (int cc = 0; cc < 3; ++cc) st->fin_Rt[r * 3 + cc] = Rm(r, cc); st->fin_Rt[9 + r] = tv[r]; }
+    st->fin_id = h;
+}
+struct FinishTerms {
+    const float4* pairs; unsigned pair_stride; float thr; const DeviceState* st;
+    __device__ __forceinline__ bool operator()(unsigned i, float (&t)[1]) const {
+        const float* Rt = st->fin_Rt;
+        const float4 s = pairs[i], q = pairs[pair_stride + i];
+        const float x = (Rt[0] * s.x + (Rt[1] * s.y + Rt[2] * s.z)) + Rt[9];
+        const float y = (Rt[3] * s.x + (Rt[4] * s.y + Rt[5] * s.z)) + Rt[10];
+        const float z = (Rt[6] * s.x + (Rt[7] * s.y + Rt[8] * s.z)) + Rt[11];
+        const float dx = x - q.x, dy = y - q.y, dz = z - q.z;
+        const float err = sqrtf(dx * dx + (dy * dy + dz * dz));
+        const bool in = err < thr;                            // registration.cpp:275
+        t[0] = in ? err * err : 0.0f;                         // total_error += err * err, :277
+        return in;
+    }
+};
+__global__ void __launch_bounds__(ess::kChainThreads)
+finish_tail_kernel(const float* __restrict__ terms, const ess::BlockSummary* __restrict__ summ, unsigned n, float n_src_f, DeviceState* __restrict__ st) {
+    float* out = st->out18;
+    if (st->fin_none) {
+        if (threadIdx.x < 16) out[threadIdx.x] = (threadIdx.x % 5 == 0) ? 1.0f : 0.0f;
+        if (threadIdx.x == 16) { out[16] = 0.0f; out[17] = 0.0f; out[18] = __int_as_float(-1); }
+        return;
+    }
+    extern __shared__ __align__(128) unsigned char ess_smem[];
+    ess::ChainSmem& sm = *reinterpret_cast<ess::ChainSmem*>(ess_smem);
+    const float total = ess::chain(terms, summ, n, sm, nullptr);
+    if (threadIdx.x != 0) return;
+    const int inliers = (int)st->seq_count;                   // recounted here: the winner may have been scored on another rank
+    const float* Rt = st->fin_Rt;
+    for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) out[c * 4 + r] = Rt[r * 3 + c]; out[12 + r] = Rt[9 + r]; out[r * 4 + 3] = 0.0f; }
+    out[15] = 1.0f;
+    out[16] = (float)inliers / n_src_f;                       // registration.cpp:281
+    out[17] = inliers > 0 ? sqrtf(total / (float)inliers) : 999.0f;
+    out[18] = __int_as_float(st->fin_id);
 }
 
 // ---------------------------------------------------------------------------------
@@ -976,6 +1064,25 @@ int ransac_reduce_impl(b3d_ctx* c, int h0, int h1, const int64_t* limit_key_dev,
     return B3D_OK;
 }
 
+// Sharded selection: keys3[0] = best over ids of [h0,h1) up to this range's own first exit, keys3[1] = that exit key (0: none),
+// keys3[2] = best over all ids of the range.  Two launches, no host synchronisation.
+int ransac_reduce3_impl(b3d_ctx* c, int h0, int h1, unsigned long long* keys3) {
+    if (!c->prepared) return fail(c, B3D_ERR_STATE, "ransac_reduce: call ransac_prepare first");
+    if (h0 < 0 || h1 > c->H || h0 > h1 || !keys3) return fail(c, B3D_ERR_INVALID, "ransac_reduce: bad arguments");
+    StageTimer timer(c, 3);
+    B3D_CUDA(c, cudaMemsetAsync(keys3, 0, 3 * sizeof(unsigned long long), c->stream));
+    if (h1 > h0 && c->n_src) {
+        const float n_src_f = (float)c->n_src;
+        const int blocks = grid_for(h1 - h0, 256, 4);
+        select_kernel<<<blocks, 256, 0, c->stream>>>(c->counts.as<int>(), h0, h1, n_src_f, c->confidence, 2, nullptr, keys3 + 1);
+        B3D_LAUNCHED(c);
+        select_kernel<<<blocks, 256, 0, c->stream>>>(c->counts.as<int>(), h0, h1, n_src_f, c->confidence, 1,
+                                                     reinterpret_cast<const long long*>(keys3 + 1), keys3);
+        B3D_LAUNCHED(c);
+    }
+    return B3D_OK;
+}
+
 int ransac_finish_impl(b3d_ctx* c, const int64_t* keys_dev, float* T, float* fitness, float* rmse, int32_t* best) {
     if (!c->prepared || !keys_dev) return fail(c, B3D_ERR_STATE, "ransac_finish: not prepared");
     DeviceState* st = c->state.as<DeviceState>();
@@ -984,11 +1091,35 @@ int ransac_finish_impl(b3d_ctx* c, const int64_t* keys_dev, float* T, float* fit
         *fitness = 0.0f; *rmse = 0.0f; if (best) *best = -1;
         return B3D_OK;
     }
-    {
+    if (c->finish_mode == 1) {
         StageTimer timer(c, 3);
         finish_kernel<<<1, kFinishThreads, 0, c->stream>>>(reinterpret_cast<const long long*>(keys_dev), c->draws.as<uint32_t>(),
                                                            c->pairs.as<float4>(), (unsigned)c->n_src, c->pair_stride,
                                                            (float)c->n_src, c->ransac_thr, st);
+        B3D_LAUNCHED(c);
+    } else {
+        const unsigned n = (unsigned)c->n_src;
+        const size_t stride = ess::padded_terms(n);
+        B3D_CUDA(c, c->ess_terms.ensure(sizeof(float) * stride));
+        B3D_CUDA(c, c->ess_bsum.ensure(sizeof(double) * (stride / ess::kBlock)));
+        B3D_CUDA(c, c->ess_guess.ensure(sizeof(double) * (stride / ess::kSuperTerms)));
+        B3D_CUDA(c, c->ess_summ.ensure(sizeof(ess::BlockSummary) * (stride / ess::kBlock)));
+        if (!c->fin_smem_opt_in) {
+            B3D_CUDA(c, cudaFuncSetAttribute(finish_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ess::ChainSmem)));
+            c->fin_smem_opt_in = true;
+        }
+        StageTimer timer(c, 3);
+        finish_head_kernel<<<1, 32, 0, c->stream>>>(reinterpret_cast<const long long*>(keys_dev), c->draws.as<uint32_t>(), c->pairs.as<float4>(), c->pair_stride, st);
+        B3D_LAUNCHED(c);
+        FinishTerms fn{c->pairs.as<float4>(), c->pair_stride, c->ransac_thr, st};
+        const int term_blocks = div_up(n, ess::kTermsThreads);
+        ess::terms_kernel<1><<<term_blocks, ess::kTermsThreads, 0, c->stream>>>(fn, n, &st->fin_none, c->ess_terms.as<float>(), stride, c->ess_bsum.as<double>(),
+                                                                                 c->ess_guess.as<double>(), &st->seq_count);
+        B3D_LAUNCHED(c);
+        ess::summary_kernel<<<dim3((unsigned)div_up(term_blocks, ess::kSummaryWarps), 1), ess::kSummaryWarps * 32, 0, c->stream>>>(
+            c->ess_terms.as<float>(), stride, c->ess_bsum.as<double>(), c->ess_guess.as<double>(), n, &st->fin_none, c->ess_summ.as<ess::BlockSummary>());
+        B3D_LAUNCHED(c);
+        finish_tail_kernel<<<1, ess::kChainThreads, sizeof(ess::ChainSmem), c->stream>>>(c->ess_terms.as<float>(), c->ess_summ.as<ess::BlockSummary>(), n, (float)c->n_src, st);
         B3D_LAUNCHED(c);
     }
     B3D_CUDA(c, cudaMemcpyAsync(c->h_state->out18, st->out18, sizeof(float) * 20, cudaMemcpyDeviceToHost, c->stream));

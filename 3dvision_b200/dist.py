@@ -1,19 +1,21 @@
-"""Hypothesis / row sharding of ransacRegistration over torch.distributed (one process per GPU).
+"""Multi-GPU helpers (one process per GPU).
 
-The reference has no multi-GPU code; this is the §8(e) design:
-  * descriptor matching: source rows split across ranks, index slices combined with one
-    all-reduce (each rank contributes zeros outside its slice);
-  * hypotheses: rank g scores ids [g*H/G, (g+1)*H/G) against the replicated pair array;
-  * selection: two 8-byte MAX all-reduces reproduce the sequential rule of
-    registration.cpp:284-290 exactly —
-      keys[1] = 0xFFFFFFFF - (first id with fitness > confidence)   (early exit)
-      keys[0] = (fitness_bits << 32) | (0xFFFFFFFF - id), restricted to ids <= that exit id
-    so the winner is (max fitness, min id) among the iterations the reference would have run;
-  * the winner's transform / fitness / rmse are recomputed on every rank from its id.
+The sharded hot path itself lives behind the C-ABI (csrc/b3d_dist.cu: ``b3d_ransac_sharded``,
+``b3d_register_scene_sharded``; NCCL called from C, no Python on the data path).  What is here:
+
+  * ``init_comm``: hands rank 0's ``ncclUniqueId`` to the other ranks of a torch.distributed group and calls
+    ``b3d_comm_init`` — torch.distributed is only the bootstrap (a C++ host would use MPI, a file or its own pool);
+  * ``sharded_ransac`` + ``resolve_keys``: a line-for-line mirror of the C protocol over a small backend interface, so
+    the selection logic can be tested at world_size 2 over gloo on a CPU box with an oracle-backed stand-in
+    (tests/test_dist_gloo.py).  The protocol:
+      - descriptor matching: source rows in contiguous chunks of ceil(n/G), index slices all-gathered;
+      - hypotheses: rank g scores ids [g*ceil(H/G), (g+1)*ceil(H/G)) against the replicated pair array;
+      - selection: ONE all-gather of three keys per rank — the rank's first id with fitness > confidence, its best key
+        over all its ids, its best key over ids up to that exit — from which every rank resolves the sequential rule of
+        registration.cpp:284-290 locally (ranges are contiguous and ordered by rank);
+      - the winner's transform / fitness / rmse are recomputed on every rank from its id;
+  * ``sharded_batch``: batched multi-object registration, instance i -> rank i mod G, no data-path collective.
 Single-cloud ICP does not shard ("replicas only").
-
-The protocol is written against a small backend interface so the same code runs over NCCL
-with the CUDA context and over gloo with a CPU stand-in in the tests.
 """
 from __future__ import annotations
 
@@ -23,8 +25,11 @@ import torch.distributed as dist
 
 
 def shard_range(total: int, rank: int, world: int):
-    """Contiguous, balanced [lo, hi) of `total` items for `rank` of `world`."""
-    return (total * rank) // world, (total * (rank + 1)) // world
+    """Contiguous [lo, hi) of `total` items for `rank` of `world`: chunks of ceil(total / world), as b3d_dist.cu deals
+    rows and hypothesis ids (equal chunks let the index slices be gathered with one ncclAllGather)."""
+    chunk = (total + world - 1) // world
+    lo = min(chunk * rank, total)
+    return lo, min(lo + chunk, total)
 
 
 def pack_best_key(fitness: float, hyp_id: int) -> int:
@@ -44,62 +49,59 @@ def pack_exit_key(hyp_id: int) -> int:
     return 0xFFFFFFFF - int(hyp_id)
 
 
-class CudaBackend:
-    """Adapter from a b3d Context (clouds + features already resident) to the protocol."""
-
-    def __init__(self, ctx, n_src: int):
-        self.ctx = ctx
-        self.n_src = n_src
-        self.keys = torch.zeros(2, dtype=torch.int64, device="cuda")
-        ctx.set_stream(torch.cuda.current_stream().cuda_stream)
-        self._corr = torch.zeros(max(n_src, 1), dtype=torch.int32, device="cuda")     # exchange buffer (uint32 bits)
-
-    def match_rows(self, r0, r1):
-        self.ctx.match_features(r0, r1)
-        self.ctx.get_correspondences_device(self._corr.data_ptr())                    # stream-ordered D2D
-        self._corr[:r0].zero_()
-        self._corr[r1:].zero_()
-        return self._corr
-
-    def correspondences_ready(self):
-        self.ctx.set_correspondences_device(self._corr.data_ptr())
-
-    def prepare(self, voxel, H, confidence):
-        self.ctx.ransac_prepare(voxel, H, confidence)
-
-    def score(self, h0, h1):
-        self.ctx.ransac_score(h0, h1)
-
-    def reduce(self, h0, h1, with_limit):
-        k = self.keys
-        self.ctx.ransac_reduce(h0, h1, k.data_ptr(), k[1:].data_ptr() if with_limit else None)
-        return k
-
-    def finish(self):
-        return self.ctx.ransac_finish(self.keys.data_ptr())
+def resolve_keys(all_keys) -> int:
+    """resolve_keys_kernel of b3d_dist.cu: all_keys[r] = (best up to r's own exit, r's first exit key or 0, best over all of
+    r's ids), ranks in id order.  The reference stops at the first exit: ranks before it count in full, the exit rank up
+    to its exit, later ranks not at all."""
+    best = 0
+    for up_to_exit, exit_key, overall in all_keys:
+        if exit_key:
+            return max(best, up_to_exit)
+        best = max(best, overall)
+    return best
 
 
-def sharded_ransac(backend, voxel_size: float, max_iterations: int, confidence: float, group=None,
-                   match: bool = True):
-    """Run ransacRegistration with rows and hypotheses sharded over `group`. Returns
-    (T 4x4, fitness, rmse, best_iteration) — identical on every rank."""
+def init_comm(ctx, group=None):
+    """Make `ctx` a rank of an NCCL communicator spanning `group` (b3d_comm_init); collective."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
-    if match:
-        r0, r1 = shard_range(backend.n_src, rank, world)
-        corr = backend.match_rows(r0, r1)
-        if world > 1:
-            dist.all_reduce(corr, op=dist.ReduceOp.SUM, group=group)     # disjoint slices, zeros elsewhere
-        backend.correspondences_ready()
+    if world == 1:
+        ctx.comm_init(None, 0, 1)
+        return
+    box = [ctx.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    ctx.comm_init(box[0], rank, world)
+
+
+def sharded_ransac(backend, voxel_size: float, max_iterations: int, confidence: float, group=None):
+    """Mirror of ransac_sharded_resident_impl (b3d_dist.cu) over a backend with match_rows / set_correspondences /
+    prepare / score / keys3 / finish.  Returns (T 4x4, fitness, rmse, best_iteration) — identical on every rank."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    n = backend.n_src
+    chunk = (n + world - 1) // world
+    r0, r1 = shard_range(n, rank, world)
+    mine = torch.zeros(max(chunk, 1), dtype=torch.int64)
+    if r1 > r0:
+        mine[:r1 - r0] = torch.from_numpy(np.asarray(backend.match_rows(r0, r1), np.int64))
+    if world > 1:
+        parts = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine, group=group)                          # ncclAllGather of the (padded) index slices
+        corr = torch.cat(parts)[:n]
+    else:
+        corr = mine[:n]
+    backend.set_correspondences(corr.numpy().astype(np.uint32))
     backend.prepare(voxel_size, max_iterations, confidence)
     h0, h1 = shard_range(max_iterations, rank, world)
     backend.score(h0, h1)
-    keys = backend.reduce(h0, h1, with_limit=False)
+    k3 = torch.tensor([int(k) for k in backend.keys3(h0, h1)], dtype=torch.int64)      # keys fit in 63 bits (fitness <= 1.0)
     if world > 1:
-        dist.all_reduce(keys[1:2], op=dist.ReduceOp.MAX, group=group)    # global first-exit id
-        keys = backend.reduce(h0, h1, with_limit=True)                   # best among ids <= exit id
-        dist.all_reduce(keys[0:1], op=dist.ReduceOp.MAX, group=group)
-    return backend.finish()
+        parts = [torch.zeros_like(k3) for _ in range(world)]
+        dist.all_gather(parts, k3, group=group)                            # the one selection collective: 24 bytes per rank
+        all_keys = [tuple(int(v) for v in p) for p in parts]
+    else:
+        all_keys = [tuple(int(v) for v in k3)]
+    return backend.finish(resolve_keys(all_keys))
 
 
 def sharded_batch(instances, run_one, group=None, device="cpu"):

@@ -142,9 +142,20 @@ int b3d_ransac_score(b3d_ctx* ctx, int h0, int h1);
  * Both combine across ranks with MAX.  If limit_key_dev != NULL it points to a
  * reduced keys[1]; only ids <= that first-exit id are considered for keys[0]. */
 int b3d_ransac_reduce(b3d_ctx* ctx, int h0, int h1, const int64_t* limit_key_dev, int64_t* keys_dev);
+/* The sharded form of the selection (what b3d_ransac_sharded gathers): three keys for ids [h0,h1) in one call,
+ *   keys3[0] = best key over the ids up to this range's own first exit (all of them if it has none)
+ *   keys3[1] = 0xFFFFFFFF - (first id of the range with fitness > confidence)   (0 if none)
+ *   keys3[2] = best key over all ids of the range.
+ * With the ranges of all ranks in id order the global result is: scan ranks, max of keys3[2] until the first rank with
+ * keys3[1] != 0, whose keys3[0] enters the max last. */
+int b3d_ransac_reduce3(b3d_ctx* ctx, int h0, int h1, int64_t* keys3_dev);
 /* Recomputes the winner's transform/fitness/rmse from the globally reduced keys[0]. */
 int b3d_ransac_finish(b3d_ctx* ctx, const int64_t* keys_dev,
                       float out_T_colmajor[16], float* out_fitness, float* out_rmse, int32_t* out_best_iteration);
+/* How b3d_ransac_finish forms the winner's rmse, i.e. the reference's sequential fp32 sum of err^2 over the inliers
+ * (src/registration.cpp:277): 0 (default) = the parallel exact-summation scheme (csrc/b3d_ess.cuh), 1 = one dependent
+ * add per inlier (the older kernel, kept to cross-check).  Both return the same bits. */
+int b3d_set_finish_mode(b3d_ctx* ctx, int mode);
 /* Parity taps: per-hypothesis inlier counts (-1 degenerate triple, -2 not scored /
  * after early exit) and (R row-major 9, t 3) per hypothesis. */
 int b3d_ransac_counts(b3d_ctx* ctx, int h0, int h1, int32_t* out_host);
@@ -246,6 +257,37 @@ int b3d_icp_run(b3d_ctx* ctx, const float T0_colmajor[16], float distance_thresh
  * source point under T within distance_threshold.  idx = B3D_NO_MATCH where none. */
 int b3d_icp_nearest(b3d_ctx* ctx, const float T_colmajor[16], float distance_threshold,
                     uint32_t* out_idx_host, float* out_d2_host);
+
+/* ---- multi-GPU: one process (or host thread) per GPU, NCCL over NVLink --------------------------------
+ * The two parts of the path that shard: feature-matching rows (one in-place ncclAllGather of the index slices) and RANSAC
+ * hypothesis ids (contiguous ranges; one ncclAllGather of three 64-bit keys per rank, from which every rank resolves the
+ * reference's sequential selection — strict-> best, break at the first id with fitness > confidence,
+ * src/registration.cpp:281-290 — and rebuilds the winner from its index triple).  Results are identical on every rank
+ * and identical to the single-GPU call.  Batched multi-object work needs no collective (one context per instance, any
+ * device); single-cloud ICP stays on one GPU.  NCCL is bound at run time (libnccl.so.2), there is no link-time dependency.
+ *
+ * b3d_comm_unique_id: ncclGetUniqueId into 128 caller bytes (rank 0 calls it and hands the bytes to the other ranks by
+ * whatever the host program uses: MPI, a file, torch.distributed, shared memory between pool threads).
+ * b3d_comm_init: ncclCommInitRank on the context's device; collective over all `world` ranks.  world == 1 is a no-op group.
+ * b3d_comm_attach: use a communicator the host program already owns (an ncclComm_t) instead; never destroyed by us. */
+int b3d_comm_unique_id(void* out_id128);
+int b3d_comm_init(b3d_ctx* ctx, const void* id128, int rank, int world);
+int b3d_comm_attach(b3d_ctx* ctx, void* nccl_comm, int rank, int world);
+int b3d_comm_destroy(b3d_ctx* ctx);
+/* Registration::ransacRegistration (include/registration.hpp:40-48) called collectively by every rank with the SAME host
+ * inputs; each rank uploads the clouds, the target descriptors and only its own rows of the source descriptors. */
+int b3d_ransac_sharded(b3d_ctx* ctx, const float* src_xyz, size_t n_src, const float* tgt_xyz, size_t n_tgt,
+                       const float* src_desc, const float* tgt_desc, float voxel_size, int max_iterations, float confidence,
+                       float out_T_colmajor[16], float* out_fitness, float* out_rmse, int32_t* out_best_iteration);
+/* The same on inputs already resident (b3d_set_clouds + b3d_set_features on every rank); match_features == 0 uses the
+ * correspondences set by b3d_set_correspondences instead of matching. */
+int b3d_ransac_sharded_resident(b3d_ctx* ctx, float voxel_size, int max_iterations, float confidence, int match_features,
+                                float out_T_colmajor[16], float* out_fitness, float* out_rmse, int32_t* out_best_iteration);
+/* b3d_register_scene called collectively: every rank runs the front end on the whole scene, matching and scoring are
+ * sharded as above, the refinement runs on every rank from the common coarse pose. */
+int b3d_register_scene_sharded(b3d_ctx* ctx, const float* scene_xyz, size_t n, float voxel_size, int normals_k, float fpfh_radius,
+                               int ransac_max_iterations, float ransac_confidence, float icp_distance_threshold, int icp_max_iterations,
+                               int point_to_plane, b3d_scene_result* out);
 
 /* ---- instrumentation ---------------------------------------------------------------- */
 /* Number of kernels this context has launched since creation (bench.py: gpu_launches). */

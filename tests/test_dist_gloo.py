@@ -1,8 +1,9 @@
 """world_size-2 gloo tests of the hypothesis/row sharding protocol (3dvision_b200/dist.py) on CPU.
 
 The CUDA context is replaced by a stand-in that answers each backend call from the oracle, so the
-code under test is exactly the host-side protocol the NCCL path runs: disjoint-slice all-reduce of
-correspondences, the packed (fitness, id) MAX key, and the early-exit restriction."""
+code under test is the protocol the NCCL path runs behind the C-ABI (csrc/b3d_dist.cu), mirrored line for line in
+dist.py: all-gather of the correspondence slices, one all-gather of three packed keys per rank, and the local
+resolution of the reference's sequential best / early-exit rule."""
 import importlib
 import os
 import socket
@@ -21,17 +22,12 @@ class OracleBackend:
     def __init__(self, case):
         from oracle import oracle as O
         self.O = O; self.case = case; self.n_src = case.source.shape[0]
-        self.keys = torch.zeros(2, dtype=torch.int64)
 
     def match_rows(self, r0, r1):
-        corr = np.zeros(self.n_src, np.int32)
-        if r1 > r0:
-            corr[r0:r1] = self.O.match_features(self.case.source_desc, self.case.target_desc, r0, r1).astype(np.int32)
-        self._corr_t = torch.from_numpy(corr)
-        return self._corr_t
+        return self.O.match_features(self.case.source_desc, self.case.target_desc, r0, r1)
 
-    def correspondences_ready(self):
-        self.corr = self._corr_t.numpy().astype(np.uint32)
+    def set_correspondences(self, corr):
+        self.corr = np.asarray(corr, np.uint32)
 
     def prepare(self, voxel, H, confidence):
         self.voxel, self.H, self.conf = voxel, H, confidence
@@ -40,32 +36,28 @@ class OracleBackend:
         r = self.O.ransac(self.case.source, self.case.target, self.corr, self.voxel, self.H, 2.0, iter_lo=h0, iter_hi=h1, want_counts=True)
         self.counts = r.extra["counts"]
 
-    def reduce(self, h0, h1, with_limit):
+    def keys3(self, h0, h1):
+        """ransac_reduce3_impl: (best over ids up to this range's own first exit, that exit key, best over all ids)."""
         n = np.float32(self.n_src)
-        limit = 0xFFFFFFFF
-        if with_limit and int(self.keys[1]) != 0:
-            limit = 0xFFFFFFFF - int(self.keys[1])
-        best, exit_key = 0, 0
+        exit_key, overall = 0, 0
         for h in range(h0, h1):
             c = int(self.counts[h])
             if c <= 0:
                 continue
             fit = np.float32(c) / n
-            if not with_limit and fit > np.float32(self.conf):
+            if fit > np.float32(self.conf):
                 exit_key = max(exit_key, bdist.pack_exit_key(h))
-        if not with_limit:
-            self.keys[1] = exit_key
-            if exit_key:
-                limit = 0xFFFFFFFF - exit_key
+            overall = max(overall, bdist.pack_best_key(fit, h))
+        limit = 0xFFFFFFFF - exit_key if exit_key else 0xFFFFFFFF
+        up_to = 0
         for h in range(h0, h1):
             c = int(self.counts[h])
             if c > 0 and h <= limit:
-                best = max(best, bdist.pack_best_key(np.float32(c) / n, h))
-        self.keys[0] = best
-        return self.keys
+                up_to = max(up_to, bdist.pack_best_key(np.float32(c) / n, h))
+        return up_to, exit_key, overall
 
-    def finish(self):
-        fit, hid = bdist.unpack_best_key(int(self.keys[0]))
+    def finish(self, best_key):
+        fit, hid = bdist.unpack_best_key(int(best_key))
         if hid < 0:
             return np.eye(4, dtype=np.float32), 0.0, 0.0, -1
         ok, R, t, _ = self.O.ransac_hypothesis(self.case.source, self.case.target, self.corr, hid)
@@ -107,7 +99,20 @@ def test_shard_range_partitions_exactly():
             r = [bdist.shard_range(total, k, world) for k in range(world)]
             assert r[0][0] == 0 and r[-1][1] == total
             assert all(r[k][1] == r[k + 1][0] for k in range(world - 1))
-            assert max(b - a for a, b in r) - min(b - a for a, b in r) <= 1
+            chunk = -(-total // world)
+            assert all(b - a <= chunk for a, b in r) and all(b - a == chunk for a, b in r if b < total)    # equal chunks: one all-gather
+
+
+def test_resolve_keys_follows_the_sequential_rule():
+    k, e = bdist.pack_best_key, bdist.pack_exit_key
+    # no exit anywhere: plain maximum (highest fitness, then lowest id)
+    assert bdist.resolve_keys([(k(0.2, 5), 0, k(0.2, 5)), (k(0.4, 130), 0, k(0.4, 130)), (k(0.4, 250), 0, k(0.4, 250))]) == k(0.4, 130)
+    # rank 1 exits at id 140: rank 0 counts in full, rank 1 only up to 140, rank 2 (which holds a better pose) never ran
+    keys = [(k(0.3, 7), 0, k(0.3, 7)), (k(0.6, 140), e(140), k(0.9, 180)), (k(0.95, 210), e(205), k(0.95, 210))]
+    assert bdist.resolve_keys(keys) == k(0.6, 140)
+    # an earlier rank's best survives if the exit hypothesis is not better than it (cannot happen with one confidence, still the rule)
+    assert bdist.resolve_keys([(k(0.7, 3), 0, k(0.7, 3)), (k(0.65, 120), e(120), k(0.65, 120))]) == k(0.7, 3)
+    assert bdist.resolve_keys([(0, 0, 0), (0, 0, 0)]) == 0
 
 
 def test_key_packing_orders_like_the_sequential_rule():

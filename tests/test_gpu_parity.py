@@ -377,3 +377,18 @@ def test_host_features_drop_the_resident_model(b3d, ctx):
     with pytest.raises(b3d.B3DError) as e:
         ctx.register_scene(model, 0.01, 30, 0.05, 100, 0.999, 0.004, 5, True)
     assert e.value.status == b3d._capi.B3D_ERR_STATE
+
+
+def test_ransac_rmse_parallel_exact_sum_equals_the_one_chain_kernel(ctx, oracle):
+    """finish mode 0 (default, csrc/b3d_ess.cuh) and mode 1 (one dependent add per inlier): same bits, equal to the oracle."""
+    c = syn.ransac_case(n_src=40_000, n_tgt=20_000, seed=71, max_iterations=500, inlier_frac=0.5)
+    res = []
+    for mode in (0, 1):
+        ctx.set_finish_mode(mode)
+        try:
+            res.append(ctx.ransac(c.source, c.target, c.source_desc, c.target_desc, c.voxel_size, 500, 0.999))
+        finally:
+            ctx.set_finish_mode(0)
+    assert np.array_equal(res[0][0], res[1][0]) and res[0][1:] == res[1][1:]
+    ref = oracle.ransac_registration(c.source, c.target, c.source_desc, c.target_desc, c.voxel_size, 500, 0.999)
+    assert np.array_equal(res[0][0], ref.transformation) and res[0][1] == ref.fitness and res[0][2] == ref.rmse
