@@ -33,7 +33,7 @@ SYMBOLS = [
     "b3d_correspondences_devptr", "b3d_set_score_mode", "b3d_ransac_prepare", "b3d_ransac_score", "b3d_ransac_reduce", "b3d_ransac_reduce3", "b3d_ransac_finish", "b3d_set_finish_mode",
     "b3d_ransac_counts", "b3d_ransac_hypotheses", "b3d_set_icp_mode", "b3d_icp_run", "b3d_icp_nearest",
     "b3d_kernel_launches", "b3d_stage_ms", "b3d_measure_fp32_rate", "b3d_score_recounts", "b3d_icp_exact_sum_stats",
-    "b3d_prepare_model", "b3d_register_scene", "b3d_register_scene_device", "b3d_depth_to_cloud", "b3d_register_depth", "b3d_world_poses", "b3d_filter_duplicates", "b3d_voxel_downsample", "b3d_set_voxel_order_mode", "b3d_estimate_normals", "b3d_compute_fpfh",
+    "b3d_prepare_model", "b3d_register_scene", "b3d_register_scene_device", "b3d_depth_to_cloud", "b3d_register_depth", "b3d_world_poses", "b3d_filter_duplicates", "b3d_voxel_downsample", "b3d_estimate_normals", "b3d_compute_fpfh",
 ]
 
 
@@ -115,7 +115,6 @@ def _declare(L):
     L.b3d_score_recounts.argtypes = [_vp, C.POINTER(C.c_uint64)]
     L.b3d_icp_exact_sum_stats.argtypes = [_vp, C.POINTER(C.c_uint32)]
     L.b3d_voxel_downsample.argtypes = [_vp, _vp, C.c_size_t, _vp, C.c_float, _vp, _vp, C.c_size_t, C.POINTER(C.c_size_t)]
-    L.b3d_set_voxel_order_mode.argtypes = [_vp, C.c_int]
     L.b3d_depth_to_cloud.argtypes = [_vp, _vp, C.c_int, C.c_int, _vp, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                                      C.c_float, _vp, _vp, _vp, C.c_size_t, C.POINTER(C.c_size_t)]
     L.b3d_register_depth.argtypes = [_vp, _vp, C.c_int, C.c_int, _vp, C.c_int, C.c_int] + [C.c_float] * 6 + [C.c_float, C.c_int, C.c_float, C.c_int,
@@ -501,10 +500,6 @@ class Context:
         self._check(self._L.b3d_voxel_downsample(self._h, _ptr(xyz), n, _ptr(col) if col is not None else None, voxel_size,
                                                  _ptr(out), _ptr(out_col) if out_col is not None else None, n, C.byref(m)))
         return out[:m.value].copy(), (out_col[:m.value].copy() if out_col is not None else None)
-
-    def set_voxel_order_mode(self, mode: int):
-        """0 (default): unordered_map order replayed on the device; 1: real container on the host (cross-check)."""
-        self._check(self._L.b3d_set_voxel_order_mode(self._h, mode))
 
     def estimate_normals(self, xyz, k=30):
         xyz = _as_f32(xyz, 3)

@@ -315,12 +315,6 @@ int b3d_filter_duplicates(b3d_ctx* c, const float* poses, size_t n, float min_di
     return filter_duplicates_impl(c, poses, n, min_distance, out_poses, out_n);
 }
 
-int b3d_set_voxel_order_mode(b3d_ctx* c, int mode) {
-    if (!c || mode < 0 || mode > 1) return B3D_ERR_INVALID;
-    c->voxel_order_mode = mode;
-    return B3D_OK;
-}
-
 int b3d_estimate_normals(b3d_ctx* c, const float* xyz, size_t n, int k, float* out_normals) {
     if (!c || (n && (!xyz || !out_normals))) return B3D_ERR_INVALID;
     B3D_CUDA(c, enter(c));

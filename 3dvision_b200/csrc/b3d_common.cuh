@@ -129,7 +129,6 @@ struct b3d_ctx {
     static constexpr int kFeatureBufs = 48;
     b3d::DevBuf fbuf[kFeatureBufs];
     bool model_ready = false;                // b3d_prepare_model has left the target cloud / normals / FPFH resident
-    int voxel_order_mode = 0;                // 0: container order simulated on the device; 1: real std::unordered_map on the host
 
     // multi-GPU (b3d_dist.cu): communicator of the group this context is a rank of
     void* comm = nullptr;                    // ncclComm_t

@@ -53,6 +53,8 @@ constexpr int kBlock = 32;                    // terms per block summary
 constexpr int kSuper = 32;                    // block summaries per super-block (one per lane)
 constexpr int kSuperTerms = kBlock * kSuper;  // 512
 constexpr unsigned kFail = 0x80000000u;       // BlockSummary::tag bit: this block must be added term by term
+constexpr unsigned kZeroOnZero = 0x40000000u; // BlockSummary::tag value: every term of the block is +-0 and the guessed running sum is 0 —
+                                              // a no-op while the true sum is +0 (leading skipped records, sums that never leave zero)
 constexpr int kV23 = 1 << 23, kV24 = 1 << 24, kV25 = 1 << 25;
 constexpr int kMarginSlack = 8;               // covers the start offsets r <= 3 and the rounding of the fp64 position estimate
 
@@ -165,6 +167,13 @@ B3D_HD bool choose_second(unsigned tag_a, unsigned tag_b, unsigned predecessor) 
     if (!(tag_a & kFail) && tag_a == predecessor) return false;
     if (!(tag_b & kFail) && tag_b == predecessor) return true;
     return (tag_a & kFail) && !(tag_b & kFail);
+}
+
+// The zero-on-zero case (no frame exists around 0): true iff the guess is 0 and all m terms are zero.
+B3D_HD bool block_is_zero_on_zero(const float* x, int m, float guess) {
+    if ((f2u(guess) & 0x7FFFFFFFu) != 0u || m <= 0) return false;
+    for (int i = 0; i < m; ++i) if ((f2u(x[i]) & 0x7FFFFFFFu) != 0u) return false;
+    return true;
 }
 
 // h of a block: its advance minus the step of the guess to the next block, so that offsets from the guesses chain up:
@@ -290,8 +299,11 @@ static __global__ void __launch_bounds__(kSummaryWarps * 32) summary_kernel(cons
 #pragma unroll
         for (int q = 0; q < kBlock / 4; ++q) { const float4 t = src[q]; x[4 * q] = t.x; x[4 * q + 1] = t.y; x[4 * q + 2] = t.z; x[4 * q + 3] = t.w; }
         const int m = (int)min((unsigned)kBlock, n - b * kBlock);
-        r = block_summary(x, m, guess, frame_of(guess));
-        r2 = block_summary(x, m, guess, other_frame_of(guess));
+        if (block_is_zero_on_zero(x, m, guess)) { r.tag = kZeroOnZero; r2.tag = kZeroOnZero; }
+        else {
+            r = block_summary(x, m, guess, frame_of(guess));
+            r2 = block_summary(x, m, guess, other_frame_of(guess));
+        }
     }
     {   // in block order: keep the predecessor's frame where it works (32 cheap steps; the summaries above were the work)
         unsigned cur = kFail;
@@ -385,6 +397,12 @@ __device__ __forceinline__ void walk_super(Running& run, const int4 qa, const in
     h.tag_a = __shfl_sync(0xffffffffu, tag, 0); h.Vg_a = __shfl_sync(0xffffffffu, Vg, 0); h.Fa = make_int4(0, 0, 0, 0);
     while (a < cnt) {
         ++rounds;
+        if (h.tag_a == kZeroOnZero && !run.units && f2u(run.s) == 0u) {      // a run of all-zero blocks on a sum that is still +0: no-ops
+            const unsigned other = __ballot_sync(0xffffffffu, lane >= a && lane < cnt && tag != kZeroOnZero);
+            a = other ? (unsigned)__ffs(other) - 1u : cnt;
+            if (a < cnt) h = round_head(a, tag, Vg, qf);
+            continue;
+        }
         int Vs = run.V;
         bool inside = run.units && run.tag == h.tag_a;
         if (!inside) inside = to_units(f2u(running_float(run)), h.tag_a, Vs);

@@ -444,19 +444,6 @@ __global__ void gather_voxels_kernel(const float* __restrict__ mean, const float
     if (mean_col) { out_col[3 * (size_t)pos] = mean_col[3 * v]; out_col[3 * (size_t)pos + 1] = mean_col[3 * v + 1]; out_col[3 * (size_t)pos + 2] = mean_col[3 * v + 2]; }
 }
 
-// The reference's key type and hash (registration.cpp:15-27), fed to the same libstdc++ container so that the
-// iteration order — bucket counts, rehash points and node placement included — is the reference's own.
-struct VoxKey { int x, y, z; bool operator==(const VoxKey& o) const { return x == o.x && y == o.y && z == o.z; } };
-struct VoxKeyHash {
-    size_t operator()(const VoxKey& k) const {
-        const std::hash<int> hi;
-        size_t h = hi(k.x);
-        h ^= hi(k.y) + 0x9e3779b9 + (h << 6) + (h >> 2);
-        h ^= hi(k.z) + 0x9e3779b9 + (h << 6) + (h >> 2);
-        return h;
-    }
-};
-
 // ---- iteration order of libstdc++'s unordered_map, computed on the device --------------------------------------
 // A node enters the container's singly linked list either right behind the "before" node of its bucket (bucket
 // already in use: it becomes the first node of that bucket's run) or at the global head (bucket empty).  A rehash
@@ -783,19 +770,8 @@ int voxel_downsample_dev(b3d_ctx* c, const float* d_xyz, unsigned n, const float
     c->launches += 4;
     gather_keys_kernel<<<div_up(m, 256), 256, 0, c->stream>>>(key3, order, m, key3_ordered);
     B3D_LAUNCHED(c);
-    if (c->voxel_order_mode == 1) {                                                 // cross-check path: the real container on the host
-        std::vector<int> h_keys(3 * (size_t)m);
-        B3D_CUDA(c, cudaMemcpyAsync(h_keys.data(), key3_ordered, sizeof(int) * 3 * m, cudaMemcpyDeviceToHost, c->stream));
-        B3D_CUDA(c, cudaStreamSynchronize(c->stream));
-        std::vector<unsigned> perm; perm.reserve(m);
-        {
-            std::unordered_map<VoxKey, unsigned, VoxKeyHash> grid;                  // no reserve(): the reference does not either
-            for (unsigned r = 0; r < m; ++r) grid.emplace(VoxKey{h_keys[3 * (size_t)r], h_keys[3 * (size_t)r + 1], h_keys[3 * (size_t)r + 2]}, r);
-            for (const auto& kv : grid) perm.push_back(kv.second);
-        }
-        B3D_CUDA(c, cudaMemcpyAsync(c->fbuf[F_PERM].p, perm.data(), sizeof(unsigned) * m, cudaMemcpyHostToDevice, c->stream));
-        B3D_CUDA(c, cudaStreamSynchronize(c->stream));                              // perm is a local
-    } else {
+    {   // the container's iteration order, replayed on the device (cross-checked against a real std::unordered_map by the tests,
+        // through the CPU oracle — there is no host implementation in this library)
         int rc = container_order_device(c, key3_ordered, m, c->fbuf[F_PERM].as<unsigned>());
         if (rc != B3D_OK) return rc;
     }

@@ -164,16 +164,13 @@ int b3d_ransac_hypotheses(b3d_ctx* ctx, int h0, int h1, float* out_host /* 12 pe
 /* ---- stages that feed the hot path; host buffers in and out ------------
  * Replaces Registration::voxelDownsample (include/registration.hpp:34, src/registration.cpp:29-60).
  * One output point per occupied voxel floor(p / voxel): the mean of its members added in input order,
- * emitted in the iteration order of the reference's std::unordered_map (same libstdc++ container, same
- * hash), because later stages index into this order.  colors_or_null / out_colors_or_null: averaged the
+ * emitted in the iteration order of the reference's std::unordered_map (the container's insertion / rehash rules are
+ * replayed on the device with per-rehash radix sorts, its growth schedule taken from libstdc++'s own _Prime_rehash_policy),
+ * because later stages index into this order.  colors_or_null / out_colors_or_null: averaged the
  * same way when given (normals are dropped, as in the reference).  *out_n = number of voxels; if it
  * exceeds `capacity` nothing is written and B3D_ERR_INVALID is returned (n is always enough). */
 int b3d_voxel_downsample(b3d_ctx* ctx, const float* xyz, size_t n, const float* colors_or_null, float voxel_size,
                          float* out_xyz, float* out_colors_or_null, size_t capacity, size_t* out_n);
-/* How the output order is obtained: 0 (default) = the container's insertion / rehash rules replayed on the
- * device (per-rehash radix sorts; growth schedule taken from libstdc++'s own _Prime_rehash_policy);
- * 1 = the distinct keys are pushed through a real std::unordered_map on the host (slow, cross-check). */
-int b3d_set_voxel_order_mode(b3d_ctx* ctx, int mode);
 /* Replaces Registration::estimateNormals (registration.hpp:36, src/registration.cpp:63-81, 105-130):
  * k nearest (self included) ordered by (d2, index), centroid and covariance summed in that order,
  * eigenvector of the smallest eigenvalue (Eigen SelfAdjointEigenSolver, iterative), flipped towards the

@@ -26,6 +26,13 @@ static float walk_super_host(float s, const BlockSummary* q, unsigned cnt, const
     };
     while (a < cnt) {
         st[2]++;
+        if (q[a].tag == kZeroOnZero && f2u(s) == 0u) {           // a run of all-zero blocks on a sum that is still +0
+            unsigned nxt = a;
+            while (nxt < cnt && q[nxt].tag == kZeroOnZero) ++nxt;
+            st[0] += nxt - a;
+            a = nxt;
+            continue;
+        }
         const unsigned tag_a = q[a].tag;
         const int* Fa = q[a].F;
         int Vs = 0;
@@ -74,8 +81,11 @@ extern "C" float ess_parallel_sum(const float* x, long n, long* stats) {
         BlockSummary r2 = r;
         if (b < nb) {
             const long m = (n - b * kBlock) < kBlock ? (n - b * kBlock) : kBlock;
-            r = block_summary(x + b * kBlock, (int)m, (float)run, frame_of((float)run));
-            r2 = block_summary(x + b * kBlock, (int)m, (float)run, other_frame_of((float)run));
+            if (block_is_zero_on_zero(x + b * kBlock, (int)m, (float)run)) { r.tag = kZeroOnZero; r2.tag = kZeroOnZero; }
+            else {
+                r = block_summary(x + b * kBlock, (int)m, (float)run, frame_of((float)run));
+                r2 = block_summary(x + b * kBlock, (int)m, (float)run, other_frame_of((float)run));
+            }
             run += bsum[b];
         }
         if (choose_second(r.tag, r2.tag, cur)) r = r2;

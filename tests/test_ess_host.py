@@ -157,3 +157,23 @@ def test_many_short_random_cases(ess):
         x = (rng.standard_normal(n).astype(np.float32) + bias) * scale
         a, b, _ = _both(ess, x)
         assert _same_bits(a, b)
+
+
+def test_leading_and_embedded_zero_runs(ess):
+    """Skipped records are +0 terms: long zero runs before the first term (sum still +0) and inside the sequence."""
+    rng = np.random.default_rng(15)
+    x = np.zeros(200_000, np.float32)
+    x[150_000:] = rng.random(50_000, dtype=np.float32) * np.float32(1e-6)
+    x[160_000:170_000] = 0.0
+    a, b, st = _both(ess, x)
+    assert _same_bits(a, b) and st[1] < 50                                  # the zero runs are folded, not added one by one
+    x = np.zeros(100_000, np.float32); x[99_999] = np.float32(3.5)
+    a, b, st = _both(ess, x)
+    assert _same_bits(a, b) and a == np.float32(3.5) and st[1] <= 2
+    x = np.zeros(70_000, np.float32); x[::7000] = np.float32(-0.0)          # -0 terms keep a +0 sum at +0
+    a, b, _ = _both(ess, x)
+    assert _same_bits(a, b) and a.view(np.uint32) == 0
+    h = rng.standard_normal(3000).astype(np.float32)                        # exact cancellation back to +0, then zeros, then more terms
+    x = np.concatenate([h, -h[::-1], np.zeros(5000, np.float32), h])
+    a, b, _ = _both(ess, x)
+    assert _same_bits(a, b)

@@ -37,19 +37,15 @@ def test_voxel_downsample_bit_identical_in_reference_order(ctx, oracle, n, voxel
 
 
 @pytest.mark.parametrize("n_vox", [1, 12, 13, 14, 29, 30, 59, 60, 127, 541, 2357, 5087, 5088, 20753, 20754, 100000])
-def test_voxel_order_device_replay_equals_host_container(ctx, n_vox):
+def test_voxel_order_device_replay_equals_host_container(ctx, oracle, n_vox):
     """Voxel counts straddling libstdc++'s rehash points (13, 29, 59, ... buckets): the device replay of the container's
-    insertion / rehash rules must give the order of the real std::unordered_map."""
+    insertion / rehash rules must give the order of the real std::unordered_map (the oracle runs the real container)."""
     rng = np.random.default_rng(n_vox)
     cells = rng.permutation(400000)[:n_vox]
     xyz = np.stack([cells % 100 - 50, (cells // 100) % 100 - 50, cells // 10000 - 20], 1).astype(np.float32) * np.float32(0.01) + np.float32(0.005)
     xyz = np.concatenate([xyz, xyz[rng.integers(0, n_vox, n_vox // 2)] + np.float32(0.001)])
     dev, _ = ctx.voxel_downsample(xyz, 0.01)
-    ctx.set_voxel_order_mode(1)
-    try:
-        host, _ = ctx.voxel_downsample(xyz, 0.01)
-    finally:
-        ctx.set_voxel_order_mode(0)
+    host = oracle.voxel_downsample(xyz, 0.01)
     assert dev.shape[0] == n_vox and same_bits(dev, host)
 
 
