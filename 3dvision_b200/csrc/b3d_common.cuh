@@ -68,6 +68,8 @@ struct DeviceState {
     float out18[20];                  // RANSAC result: T(16), fitness, rmse, best id (as int bits), unused
     float fin_Rt[12];                 // RANSAC finish: the winner's (R row-major, t), rebuilt from its index triple
     int fin_id, fin_none;             // the winner's id; 1 if no hypothesis had an inlier
+    int rng_starved;                  // a hypothesis needed index draws beyond the accepted-draw window (count -3)
+    int score_exit, score_exit_id;    // chunked scoring: an id with fitness > confidence has been met; the first such id
 };
 
 }  // namespace b3d

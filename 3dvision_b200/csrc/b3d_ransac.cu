@@ -78,13 +78,13 @@ __global__ void gather_pairs_kernel(const float4* __restrict__ src4, const float
 // ---------------------------------------------------------------------------------
 // hypothesis generation: hyp is SoA float[12][H]
 // ---------------------------------------------------------------------------------
-__global__ void hypothesis_kernel(const uint32_t* __restrict__ draws, const DeviceState* __restrict__ st,
+__global__ void hypothesis_kernel(const uint32_t* __restrict__ draws, DeviceState* __restrict__ st,
                                   const float4* __restrict__ pairs, unsigned pair_stride, int H, int h_lo, int h_hi,
                                   float* __restrict__ hyp, int* __restrict__ counts) {
     int h = h_lo + blockIdx.x * blockDim.x + threadIdx.x;
     if (h >= h_hi) return;
-    if ((unsigned)(3 * h + 2) >= st->accepted_total) { counts[h] = -3; return; }   // raw window too small
-    uint32_t i0 = draws[3 * h], i1 = draws[3 * h + 1], i2 = draws[3 * h + 2];
+    if ((unsigned)(3 * (unsigned)h + 2u) >= st->accepted_total) { counts[h] = -3; st->rng_starved = 1; return; }   // raw window too small: surfaced by finish
+    uint32_t i0 = draws[3 * (size_t)h], i1 = draws[3 * (size_t)h + 1], i2 = draws[3 * (size_t)h + 2];
     if (i0 == i1 || i1 == i2 || i0 == i2) {                // registration.cpp:240 `continue`
         counts[h] = -1;
 #pragma unroll
@@ -110,6 +110,21 @@ __global__ void hypothesis_kernel(const uint32_t* __restrict__ draws, const Devi
     counts[h] = 0;
 }
 
+// Early exit (registration.cpp:290): scoring runs in chunks of hypothesis ids; after each chunk this kernel looks for an id
+// whose fitness exceeds the confidence.  Once one exists the remaining chunks' kernels return at once (score_exit), and
+// mark_unscored_kernel gives every id behind the first such id the count -2 ("never ran"), as the reference's loop leaves it.
+__global__ void exit_check_kernel(const int* __restrict__ counts, int a, int b, float n_src_f, float confidence, DeviceState* __restrict__ st) {
+    const int h = a + blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= b) return;
+    const int c = counts[h];
+    if (c > 0 && (float)c / n_src_f > confidence) { atomicMin(&st->score_exit_id, h); st->score_exit = 1; }
+}
+__global__ void mark_unscored_kernel(int* __restrict__ counts, int h0, int h1, const DeviceState* __restrict__ st) {
+    const int h = h0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (h < h1 && st->score_exit && h > st->score_exit_id) counts[h] = -2;
+}
+__global__ void exit_reset_kernel(DeviceState* st) { st->score_exit = 0; st->score_exit_id = 0x7FFFFFFF; }
+
 __global__ void reset_counts_kernel(int* counts, int h0, int h1) {
     int h = h0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (h < h1 && (counts[h] > 0 || counts[h] == -4)) counts[h] = 0;      // -4: dropped by an earlier bail-out run; -1 (degenerate) stays
@@ -125,7 +140,8 @@ template <int KH>
 __global__ void __launch_bounds__(kScoreThreads)
 score_exact_kernel(const float* __restrict__ hyp, int H, int h0, int h1,
                    const float4* __restrict__ pairs, unsigned n_pairs, unsigned pair_stride, unsigned pairs_per_y,
-                   float cut, int* __restrict__ counts) {
+                   float cut, int* __restrict__ counts, const DeviceState* __restrict__ st) {
+    if (st->score_exit) return;                        // an earlier chunk met fitness > confidence: the reference broke there
     __shared__ float4 sS[kPairTile];
     __shared__ float4 sQ[kPairTile];
     const int tid = threadIdx.x;
@@ -229,6 +245,7 @@ __global__ void __launch_bounds__(kScoreThreads)
 score_screen_kernel(const float* __restrict__ hyp, int H, int h0, int h1,
                     const float4* __restrict__ pairs, unsigned pair_stride, unsigned pairs_per_y,
                     float cut, float thr, const DeviceState* __restrict__ st, int* __restrict__ counts) {
+    if (st->score_exit) return;                        // an earlier chunk met fitness > confidence: the reference broke there
     __shared__ float4 sS[kPairTile];
     __shared__ float4 sQ[kPairTile];
     const int tid = threadIdx.x;
@@ -348,6 +365,7 @@ score_screen2_kernel(const float* __restrict__ hyp, int H, int h0, int h1,
                      const float4* __restrict__ pairs, unsigned pair_stride, unsigned pairs_per_y,
                      float cut, float thr, const DeviceState* __restrict__ st, int* __restrict__ counts, ScoreSubset sub) {
     constexpr int KH = 2 * KP;
+    if (st->score_exit) return;                        // an earlier chunk met fitness > confidence: the reference broke there
     const int n_items = sub.n_list ? *sub.n_list : (h1 - h0);
     if ((int)(blockIdx.x * KH * kScoreThreads) >= n_items) return;
     unsigned r_lo = 0u, r_hi = pair_stride;
@@ -835,6 +853,7 @@ static int ensure_raw(b3d_ctx* c, size_t need) {
 int ransac_prepare_impl(b3d_ctx* c, float voxel, int max_iterations, float confidence) {
     if (!c->have_clouds || !c->have_corr) return fail(c, B3D_ERR_STATE, "ransac_prepare: clouds/correspondences not set");
     if (max_iterations < 0) return fail(c, B3D_ERR_INVALID, "ransac_prepare: max_iterations < 0");
+    if (max_iterations > (1 << 29)) return fail(c, B3D_ERR_INVALID, "ransac_prepare: max_iterations above 2^29 (3 draws per id must index 32-bit arrays)");
     if (c->n_src >= 0xFFFFFFFFull) return fail(c, B3D_ERR_INVALID, "ransac_prepare: n_src must be < 2^32 - 1");
     c->prepared = false; c->scored = false;
     c->H = max_iterations;
@@ -872,6 +891,7 @@ int ransac_prepare_impl(b3d_ctx* c, float voxel, int max_iterations, float confi
         B3D_LAUNCHED(c);
         scan_emit_kernel<<<tiles, kScanThreads, 0, c->stream>>>(accept, emit, (unsigned)window, c->scan_tmp.as<unsigned>());
         B3D_LAUNCHED(c);
+        B3D_CUDA(c, cudaMemsetAsync(&st->rng_starved, 0, sizeof(int), c->stream));
         if (attempt == 0) {
             B3D_CUDA(c, cudaMemsetAsync(&st->pair_smax_bits, 0, 2 * sizeof(unsigned), c->stream));
             gather_pairs_kernel<<<grid_for(pair_stride, 256), 256, 0, c->stream>>>(c->src4.as<float4>(), c->tgt4.as<float4>(),
@@ -985,13 +1005,7 @@ static int ransac_score_bailout(b3d_ctx* c, int h0, int h1) {
     return plan(4, p0);
 }
 
-int ransac_score_impl(b3d_ctx* c, int h0, int h1) {
-    if (!c->prepared) return fail(c, B3D_ERR_STATE, "ransac_score: call ransac_prepare first");
-    if (h0 < 0 || h1 > c->H || h0 > h1) return fail(c, B3D_ERR_INVALID, "ransac_score: bad hypothesis range");
-    c->scored = true; c->scored_lo = h0; c->scored_hi = h1;
-    if (h0 == h1 || c->n_src == 0) return B3D_OK;
-    StageTimer timer(c, 2);
-    { int rc = ransac_generate_impl(c, h0, h1); if (rc != B3D_OK) return rc; }
+static int ransac_score_range(b3d_ctx* c, int h0, int h1) {
     const unsigned n = (unsigned)c->n_src;
     const int nh = h1 - h0;
     // two hypotheses per thread (one packed FFMA2 lane pair) unless there are hardly any; the pair-range
@@ -1019,12 +1033,11 @@ int ransac_score_impl(b3d_ctx* c, int h0, int h1) {
         c->counts_pruned = false;
     }
     dim3 grid(bx, by);
-    B3D_CUDA(c, cudaMemsetAsync(&c->state.as<DeviceState>()->score_recounts, 0, sizeof(unsigned long long), c->stream));
     const float4* pairs = c->pairs.as<float4>();
     const DeviceState* st = c->state.as<DeviceState>();
     if (c->score_mode == 1) {               // reference arithmetic for every pair (verification / comparison)
-        if (KHe == 2) score_exact_kernel<2><<<grid, kScoreThreads, 0, c->stream>>>(c->hyp.as<float>(), c->H, h0, h1, pairs, n, c->pair_stride, per_y, c->ransac_cut, c->counts.as<int>());
-        else         score_exact_kernel<1><<<grid, kScoreThreads, 0, c->stream>>>(c->hyp.as<float>(), c->H, h0, h1, pairs, n, c->pair_stride, per_y, c->ransac_cut, c->counts.as<int>());
+        if (KHe == 2) score_exact_kernel<2><<<grid, kScoreThreads, 0, c->stream>>>(c->hyp.as<float>(), c->H, h0, h1, pairs, n, c->pair_stride, per_y, c->ransac_cut, c->counts.as<int>(), st);
+        else         score_exact_kernel<1><<<grid, kScoreThreads, 0, c->stream>>>(c->hyp.as<float>(), c->H, h0, h1, pairs, n, c->pair_stride, per_y, c->ransac_cut, c->counts.as<int>(), st);
     } else if (c->score_mode == 0 || c->score_mode == 3 || c->score_mode == 4) {   // packed FFMA2 screen (two hypotheses per instruction)
         if (KH == 4) score_screen2_kernel<2><<<grid, kScoreThreads, 0, c->stream>>>(c->hyp.as<float>(), c->H, h0, h1, pairs, c->pair_stride, per_y, c->ransac_cut, c->ransac_thr, st, c->counts.as<int>(), ScoreSubset{nullptr, nullptr, nullptr, 0});
         else if (KH == 2) score_screen2_kernel<1><<<grid, kScoreThreads, 0, c->stream>>>(c->hyp.as<float>(), c->H, h0, h1, pairs, c->pair_stride, per_y, c->ransac_cut, c->ransac_thr, st, c->counts.as<int>(), ScoreSubset{nullptr, nullptr, nullptr, 0});
@@ -1034,6 +1047,42 @@ int ransac_score_impl(b3d_ctx* c, int h0, int h1) {
         else         score_screen_kernel<1><<<grid, kScoreThreads, 0, c->stream>>>(c->hyp.as<float>(), c->H, h0, h1, pairs, c->pair_stride, per_y, c->ransac_cut, c->ransac_thr, st, c->counts.as<int>());
     }
     B3D_LAUNCHED(c);
+    return B3D_OK;
+}
+
+int ransac_score_impl(b3d_ctx* c, int h0, int h1) {
+    if (!c->prepared) return fail(c, B3D_ERR_STATE, "ransac_score: call ransac_prepare first");
+    if (h0 < 0 || h1 > c->H || h0 > h1) return fail(c, B3D_ERR_INVALID, "ransac_score: bad hypothesis range");
+    c->scored = true; c->scored_lo = h0; c->scored_hi = h1;
+    if (h0 == h1 || c->n_src == 0) return B3D_OK;
+    StageTimer timer(c, 2);
+    { int rc = ransac_generate_impl(c, h0, h1); if (rc != B3D_OK) return rc; }
+    const unsigned n = (unsigned)c->n_src;
+    exit_reset_kernel<<<1, 1, 0, c->stream>>>(c->state.as<DeviceState>());
+    B3D_LAUNCHED(c);
+    B3D_CUDA(c, cudaMemsetAsync(&c->state.as<DeviceState>()->score_recounts, 0, sizeof(unsigned long long), c->stream));
+    // fitness <= 1, so an exit is only possible below confidence 1: then score in chunks of ids (each >= ~2e9 pair evaluations,
+    // a millisecond) with a device-side exit flag, so a clean scene stops where the reference's loop breaks
+    const int nh_all = h1 - h0;
+    long long chunk = nh_all;
+    if (c->confidence < 1.0f && c->score_mode != 3) {
+        chunk = (long long)(2.0e9 / (double)n);
+        chunk = chunk < 16384 ? 16384 : chunk;
+        chunk = (chunk + 1023) / 1024 * 1024;
+        if (chunk * 3 / 2 >= nh_all) chunk = nh_all;           // not worth splitting
+    }
+    for (long long a = h0; a < h1; a += chunk) {
+        const int b = (int)((a + chunk < h1) ? a + chunk : h1);
+        int rc = ransac_score_range(c, (int)a, b); if (rc != B3D_OK) return rc;
+        if (chunk < nh_all) {
+            exit_check_kernel<<<div_up(b - (int)a, 256), 256, 0, c->stream>>>(c->counts.as<int>(), (int)a, b, (float)c->n_src, c->confidence, c->state.as<DeviceState>());
+            B3D_LAUNCHED(c);
+        }
+    }
+    if (chunk < nh_all) {
+        mark_unscored_kernel<<<div_up(nh_all, 256), 256, 0, c->stream>>>(c->counts.as<int>(), h0, h1, c->state.as<DeviceState>());
+        B3D_LAUNCHED(c);
+    }
     return B3D_OK;
 }
 
@@ -1123,7 +1172,11 @@ int ransac_finish_impl(b3d_ctx* c, const int64_t* keys_dev, float* T, float* fit
         B3D_LAUNCHED(c);
     }
     B3D_CUDA(c, cudaMemcpyAsync(c->h_state->out18, st->out18, sizeof(float) * 20, cudaMemcpyDeviceToHost, c->stream));
+    B3D_CUDA(c, cudaMemcpyAsync(&c->h_state->rng_starved, &st->rng_starved, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     B3D_CUDA(c, cudaStreamSynchronize(c->stream));
+    // hypotheses whose index draws fell outside the accepted-draw window were never generated (count -3): the window is sized 8 sigma
+    // above its expectation, so this is practically unreachable, but it must not pass silently
+    if (c->h_state->rng_starved) return fail(c, B3D_ERR_RNG_WINDOW, "ransac: accepted-draw window too small for this call (hypotheses were skipped)");
     for (int i = 0; i < 16; ++i) T[i] = c->h_state->out18[i];
     *fitness = c->h_state->out18[16];
     *rmse = c->h_state->out18[17];

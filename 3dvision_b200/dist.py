@@ -107,9 +107,8 @@ def sharded_ransac(backend, voxel_size: float, max_iterations: int, confidence: 
 def sharded_batch(instances, run_one, group=None, device="cpu"):
     """Batched multi-object registration over `group` (SURVEY.md §8e, configs[3]): instance i is owned by
     rank i mod G and processed there by `run_one(instance) -> (T 4x4, fitness, rmse)`; there is no
-    data-path collective.  The poses are then gathered with one SUM all-reduce of an (n,18) fp32 table
-    whose rows are zero everywhere but on the owner (disjoint rows, so SUM is a gather and the result is
-    bit-identical to the owner's).  `run_many`, if the callable has it, is used instead so a rank can
+    data-path collective.  The poses are then gathered with one all-gather of an (n,18) fp32 table, each
+    rank's rows taken from their owner (bit-identical to the owner's, -0.0 included).  `run_many`, if the callable has it, is used instead so a rank can
     overlap its instances on its own worker pool.  Returns a list of (T, fitness, rmse), same on every rank."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -124,6 +123,11 @@ def sharded_batch(instances, run_one, group=None, device="cpu"):
         table[i, 16], table[i, 17] = fit, rmse
     t = torch.from_numpy(table).to(device)
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        parts = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(parts, t, group=group)                             # a gather, not a SUM: bit patterns (-0.0 included) survive
+        for r, part in enumerate(parts):
+            rows = list(range(r, n, world))
+            if rows:
+                t[rows] = part[rows]
     table = t.cpu().numpy()
     return [(table[i, :16].reshape(4, 4).copy(), float(table[i, 16]), float(table[i, 17])) for i in range(n)]

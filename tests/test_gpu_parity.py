@@ -392,3 +392,27 @@ def test_ransac_rmse_parallel_exact_sum_equals_the_one_chain_kernel(ctx, oracle)
     assert np.array_equal(res[0][0], res[1][0]) and res[0][1:] == res[1][1:]
     ref = oracle.ransac_registration(c.source, c.target, c.source_desc, c.target_desc, c.voxel_size, 500, 0.999)
     assert np.array_equal(res[0][0], ref.transformation) and res[0][1] == ref.fitness and res[0][2] == ref.rmse
+
+
+def test_ransac_chunked_scoring_stops_where_the_reference_breaks(ctx, oracle):
+    """registration.cpp:290: a clean scene exceeds the confidence after a few iterations and the loop breaks.  Scoring runs in
+    chunks of hypothesis ids with a device-side exit flag: later chunks do no work, ids behind the exit read -2 (never ran),
+    and the result is the reference's."""
+    H = 250_000
+    c = syn.ransac_case(n_src=20_000, n_tgt=15_000, seed=77, inlier_frac=1.0, noise=0.00005, max_iterations=H)
+    corr = np.where(c.true_match >= 0, c.true_match, 0).astype(np.uint32)
+    ref = oracle.ransac(c.source, c.target, corr, c.voxel_size, H, 0.5, want_counts=True)
+    assert 0 < ref.extra["iters_run"] < 2000                                  # the reference stopped early
+    ctx.set_clouds(c.source, c.target); ctx.set_correspondences(corr)
+    ctx.ransac_prepare(c.voxel_size, H, 0.5)
+    import time
+    ctx.ransac_score(); ctx.ransac_counts(0, 8)                               # warm-up + sync
+    t0 = time.perf_counter(); ctx.ransac_score(); got = ctx.ransac_counts(); t_exit = time.perf_counter() - t0
+    assert np.array_equal(got, ref.extra["counts"])                           # -2 behind the break, like the reference's loop
+    ctx.ransac_prepare(c.voxel_size, H, 2.0)
+    ctx.ransac_score(); ctx.ransac_counts(0, 8)
+    t0 = time.perf_counter(); ctx.ransac_score(); ctx.ransac_counts(0, 8); t_full = time.perf_counter() - t0
+    assert t_exit < 0.75 * t_full                                             # the chunks behind the exit did no work
+    T, fit, rmse, best = ctx.ransac(c.source, c.target, c.source_desc, c.target_desc, c.voxel_size, H, 0.5)
+    r2 = oracle.ransac_registration(c.source, c.target, c.source_desc, c.target_desc, c.voxel_size, H, 0.5)
+    assert np.array_equal(T, r2.transformation) and fit == r2.fitness and rmse == r2.rmse
