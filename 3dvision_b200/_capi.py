@@ -25,7 +25,7 @@ NO_MATCH = 0xFFFFFFFF
 
 # every symbol include/b3d.h declares (tests check the library exports exactly these)
 SYMBOLS = [
-    "b3d_device_count", "b3d_comm_unique_id", "b3d_comm_init", "b3d_comm_attach", "b3d_comm_destroy",
+    "b3d_device_count", "b3d_pool_create", "b3d_pool_register", "b3d_pool_destroy", "b3d_comm_unique_id", "b3d_comm_init", "b3d_comm_attach", "b3d_comm_destroy",
     "b3d_ransac_sharded", "b3d_ransac_sharded_resident", "b3d_register_scene_sharded",
     "b3d_cuda_available", "b3d_ctx_create", "b3d_ctx_destroy", "b3d_ctx_set_stream", "b3d_strerror", "b3d_last_error",
     "b3d_ransac", "b3d_icp",
@@ -42,6 +42,19 @@ class SceneResult(C.Structure):
     _fields_ = [("coarse_T", C.c_float * 16), ("coarse_fitness", C.c_float), ("coarse_rmse", C.c_float),
                 ("coarse_best_iteration", C.c_int32), ("T", C.c_float * 16), ("fitness", C.c_float), ("rmse", C.c_float),
                 ("icp_iterations", C.c_int32), ("n_source_points", C.c_uint32)]
+
+
+class Instance(C.Structure):
+    """b3d_instance (include/b3d.h)."""
+    _fields_ = [("src_xyz", C.c_void_p), ("n_src", C.c_size_t), ("tgt_xyz", C.c_void_p), ("tgt_normals", C.c_void_p), ("n_tgt", C.c_size_t),
+                ("src_desc", C.c_void_p), ("tgt_desc", C.c_void_p), ("voxel_size", C.c_float), ("ransac_max_iterations", C.c_int),
+                ("ransac_confidence", C.c_float), ("icp_distance_threshold", C.c_float), ("icp_max_iterations", C.c_int), ("point_to_plane", C.c_int)]
+
+
+class InstanceResult(C.Structure):
+    """b3d_instance_result (include/b3d.h)."""
+    _fields_ = [("coarse_T", C.c_float * 16), ("coarse_fitness", C.c_float), ("coarse_rmse", C.c_float), ("T", C.c_float * 16),
+                ("fitness", C.c_float), ("rmse", C.c_float), ("icp_iterations", C.c_int32), ("status", C.c_int32)]
 
 
 class B3DError(RuntimeError):
@@ -120,6 +133,10 @@ def _declare(L):
     L.b3d_register_depth.argtypes = [_vp, _vp, C.c_int, C.c_int, _vp, C.c_int, C.c_int] + [C.c_float] * 6 + [C.c_float, C.c_int, C.c_float, C.c_int,
                                      C.c_float, C.c_float, C.c_int, C.c_int, C.POINTER(SceneResult)]
     L.b3d_world_poses.argtypes = [_vp, _vp, C.c_size_t, _vp, _vp]
+    L.b3d_pool_create.argtypes = [C.c_int, C.POINTER(C.c_int), C.c_int, C.POINTER(_vp)]
+    L.b3d_pool_register.argtypes = [_vp, C.POINTER(Instance), C.c_size_t, C.POINTER(InstanceResult)]
+    L.b3d_pool_destroy.argtypes = [_vp]
+    L.b3d_pool_destroy.restype = None
     L.b3d_comm_unique_id.argtypes = [_vp]
     L.b3d_comm_init.argtypes = [_vp, _vp, C.c_int, C.c_int]
     L.b3d_comm_attach.argtypes = [_vp, _vp, C.c_int, C.c_int]
@@ -157,6 +174,60 @@ def _T_colmajor(T) -> np.ndarray:
 
 def _T_from_colmajor(buf) -> np.ndarray:
     return np.asarray(buf, np.float32).reshape(4, 4).T.copy()
+
+
+class Pool:
+    """b3d_pool: the orchestrator's worker pool (pipeline.cpp:321-327) in C — n_workers host threads, one context each, dealt over
+    `devices`; register() runs ransacRegistration + icpRefine for every instance and returns [(coarse, refined)] in input order."""
+
+    def __init__(self, n_workers: int = 8, devices=(0,)):
+        self._L = lib()
+        devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+        h = _vp()
+        rc = self._L.b3d_pool_create(int(n_workers), devs, len(devices), C.byref(h))
+        if rc != B3D_OK:
+            raise B3DError(rc, self._L.b3d_strerror(rc).decode())
+        self._h = h
+
+    def register(self, instances):
+        """instances: iterable of dicts / objects with source, target, target_normals, source_desc, target_desc, voxel_size and
+        optional ransac_iterations, confidence, icp_threshold, icp_iterations, point_to_plane."""
+        instances = list(instances)
+        n = len(instances)
+        if n == 0:
+            return []
+        keep, items = [], (Instance * n)()
+        for it, inst in zip(items, instances):
+            g = (lambda k, d=None: inst.get(k, d)) if isinstance(inst, dict) else (lambda k, d=None: getattr(inst, k, d))
+            src = _as_f32(g("source"), 3); tgt = _as_f32(g("target"), 3)
+            nrm = _as_f32(g("target_normals"), 3) if g("target_normals") is not None else None
+            sd = _as_f32(g("source_desc"), 33); td = _as_f32(g("target_desc"), 33)
+            keep.append((src, tgt, nrm, sd, td))
+            voxel = float(g("voxel_size"))
+            thr = g("icp_threshold")
+            it.src_xyz = src.ctypes.data; it.n_src = src.shape[0]; it.tgt_xyz = tgt.ctypes.data; it.n_tgt = tgt.shape[0]
+            it.tgt_normals = nrm.ctypes.data if nrm is not None and nrm.shape[0] == tgt.shape[0] else None
+            it.src_desc = sd.ctypes.data; it.tgt_desc = td.ctypes.data
+            it.voxel_size = voxel; it.ransac_max_iterations = int(g("ransac_iterations", 100000)); it.ransac_confidence = float(g("confidence", 0.999))
+            it.icp_distance_threshold = float(voxel * 0.4 if thr is None else thr); it.icp_max_iterations = int(g("icp_iterations", 200))
+            it.point_to_plane = int(bool(g("point_to_plane", True)))
+        res = (InstanceResult * n)()
+        rc = self._L.b3d_pool_register(self._h, items, n, res)
+        if rc != B3D_OK:
+            raise B3DError(rc, self._L.b3d_strerror(rc).decode())
+        return [((_T_from_colmajor(np.array(r.coarse_T, np.float32)), r.coarse_fitness, r.coarse_rmse),
+                 (_T_from_colmajor(np.array(r.T, np.float32)), r.fitness, r.rmse, r.icp_iterations)) for r in res]
+
+    def close(self):
+        if self._h:
+            self._L.b3d_pool_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
 
 
 class Context:

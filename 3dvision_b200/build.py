@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libb3d.so")
-SOURCES = ["b3d_api.cu", "b3d_match.cu", "b3d_match_tc.cu", "b3d_ransac.cu", "b3d_icp.cu", "b3d_features.cu", "b3d_pose.cu", "b3d_dist.cu"]
+SOURCES = ["b3d_api.cu", "b3d_match.cu", "b3d_match_tc.cu", "b3d_ransac.cu", "b3d_icp.cu", "b3d_features.cu", "b3d_pose.cu", "b3d_dist.cu", "b3d_pool.cu"]
 HEADERS = ["b3d_common.cuh", "b3d_linalg.cuh", "b3d_scan.cuh", "b3d_grid.cuh", "b3d_featmath.cuh", "b3d_ess.cuh", os.path.join("..", "..", "include", "b3d.h")]
 
 # --fmad=false: the reference CPU build never contracts a*b+c (README.md:13, no -march), and
@@ -23,7 +23,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo", "--fmad=false",
     "-Xcompiler", "-fPIC,-O2,-ffp-contract=off",
-    "-shared", "-cudart", "static", "-ldl",
+    "-shared", "-cudart", "static", "-ldl", "-lpthread",
 ]
 
 

@@ -1211,7 +1211,9 @@ int icp_run_impl(b3d_ctx* c, const float* T0, float thr, int max_iter, int p2pla
             // O(27 n_tgt), a search O(n_src)): then build it after the first two iterations (before that the queries are too far
             // from the surface for the fine level to settle them); otherwise only for calls still iterating after kListsAfter
             const int lists_at = (max_iter >= 2 * kListsAfter && c->n_src >= 2 * c->n_tgt) ? 2 : kListsAfter;
-            if (((iter & 15) == 15 || iter == lists_at - 1) && iter + 1 < max_iter) {
+            // polls: after iterations 2 and 4 (a refinement behind RANSAC converges in a handful of iterations; every launch behind
+            // the convergence point would be an empty kernel), at the second level's build point, then every 16th iteration
+            if (((iter & 15) == 15 || iter == lists_at - 1 || ((iter == 2 || iter == 4) && stop_on_conv)) && iter + 1 < max_iter) {
                 B3D_CUDA(c, cudaMemcpyAsync(&c->h_state->done, &st->done, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
                 B3D_CUDA(c, cudaStreamSynchronize(c->stream));
                 if (c->h_state->done) break;

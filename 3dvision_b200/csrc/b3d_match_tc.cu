@@ -99,11 +99,11 @@ match_center_kernel(const float* __restrict__ tdesc, unsigned n, MatchAux* __res
 }
 
 template <bool IS_B>
-__global__ void match_prep_kernel(const float* __restrict__ desc, unsigned n, unsigned n_padded,
+__global__ void match_prep_kernel(const float* __restrict__ desc, unsigned n, unsigned first, unsigned n_padded,
                                   __nv_bfloat16* __restrict__ tiles, float* __restrict__ norm2, MatchAux* __restrict__ aux,
                                   unsigned* __restrict__ tile_bmax_bits) {
     constexpr int ROWS = IS_B ? kTcN : kTcM;
-    const unsigned r = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned r = first + blockIdx.x * blockDim.x + threadIdx.x;          // rows [first, n_padded): a rank packs only the row blocks it matches
     if (r >= n_padded) return;
     __align__(16) __nv_bfloat16 row[kTcK];
 #pragma unroll
@@ -426,21 +426,20 @@ int match_features_tc_impl(b3d_ctx* c, size_t row0, size_t row1) {
     B3D_CUDA(c, cudaMemsetAsync(aux, 0, sizeof(MatchAux) + sizeof(unsigned) * n_nt, c->stream));
     match_center_kernel<<<1, kDescDim * kCenterGroups, 0, c->stream>>>(c->tdesc_p, n_tgt, aux);
     B3D_LAUNCHED(c);
-    match_prep_kernel<false><<<div_up(n_rb_all * kTcM, 128), 128, 0, c->stream>>>(c->sdesc_p, n_src, n_rb_all * kTcM, c->tc_a_tiles.as<__nv_bfloat16>(),
-                                                                                  c->tc_norm2.as<float>(), aux, nullptr);
+    const unsigned rb_first = (unsigned)(row0 / kTcM);
+    const unsigned n_rb = (unsigned)div_up((long long)row1, kTcM) - rb_first;
+    match_prep_kernel<false><<<div_up(n_rb * kTcM, 128), 128, 0, c->stream>>>(c->sdesc_p, n_src, rb_first * kTcM, (rb_first + n_rb) * kTcM,
+                                                                              c->tc_a_tiles.as<__nv_bfloat16>(), c->tc_norm2.as<float>(), aux, nullptr);
     B3D_LAUNCHED(c);
-    match_prep_kernel<true><<<div_up(n_nt * kTcN, 128), 128, 0, c->stream>>>(c->tdesc_p, n_tgt, n_nt * kTcN, c->tc_b_tiles.as<__nv_bfloat16>(),
+    match_prep_kernel<true><<<div_up(n_nt * kTcN, 128), 128, 0, c->stream>>>(c->tdesc_p, n_tgt, 0u, n_nt * kTcN, c->tc_b_tiles.as<__nv_bfloat16>(),
                                                                              nullptr, aux, tile_bmax);
     B3D_LAUNCHED(c);
     match_seed_kernel<<<div_up((long long)(row1 - row0), 128), 128, 0, c->stream>>>(c->sdesc_p, c->tdesc_p, (unsigned)row0, (unsigned)row1, n_tgt,
                                                                                     c->tc_best.as<unsigned long long>());
     B3D_LAUNCHED(c);
-    const unsigned rb_first = (unsigned)(row0 / kTcM);
-    const unsigned n_rb = (unsigned)div_up((long long)row1, kTcM) - rb_first;
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!c->tc_smem_opt_in) {                                  // per device (a pool may drive several GPUs from one process)
         B3D_CUDA(c, cudaFuncSetAttribute(match_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
-        attr_set = true;
+        c->tc_smem_opt_in = true;
     }
     unsigned long long total = (unsigned long long)n_rb * n_nt;
     int grid = (int)(total < (unsigned long long)kNumSMs ? total : (unsigned long long)kNumSMs);

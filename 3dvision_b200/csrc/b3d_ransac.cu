@@ -1066,10 +1066,10 @@ int ransac_score_impl(b3d_ctx* c, int h0, int h1) {
     const int nh_all = h1 - h0;
     long long chunk = nh_all;
     if (c->confidence < 1.0f && c->score_mode != 3) {
-        chunk = (long long)(2.0e9 / (double)n);
-        chunk = chunk < 16384 ? 16384 : chunk;
-        chunk = (chunk + 1023) / 1024 * 1024;
-        if (chunk * 3 / 2 >= nh_all) chunk = nh_all;           // not worth splitting
+        long long want = (long long)(4.0e9 / (double)n);       // >= ~4e9 pair evaluations (two milliseconds) per chunk
+        want = want < 32768 ? 32768 : want;
+        const long long n_chunks = (nh_all + want - 1) / want;
+        if (n_chunks > 1) chunk = ((nh_all + n_chunks - 1) / n_chunks + 1023) / 1024 * 1024;   // equal chunks: no inefficient short tail launch
     }
     for (long long a = h0; a < h1; a += chunk) {
         const int b = (int)((a + chunk < h1) ? a + chunk : h1);

@@ -399,42 +399,58 @@ def pipeline_cpu_estimate(scene_raw, voxel, n_src, n_model, H, sample=3000):
 
 def batched_registration(b3d, bdist, syn, dev, rank, world, barrier, flush, n_instances=64, threads=8, reps=3):
     """configs[3]: 64 object instances, each ransacRegistration(H=100000, conf 0.999) + icpRefine(<=200 it), dealt
-    round-robin to the ranks (instance i -> rank i mod N), each rank driving its share from a pool of `threads`
-    workers with one context/stream each — the reference's own unit of parallelism (pipeline.cpp:321-327).
-    Host buffers in, poses out; wall clock, max over ranks."""
+    round-robin to the ranks (instance i -> rank i mod N), each rank driving its share through b3d_pool — the
+    orchestrator's worker pool (pipeline.cpp:321-327) behind the C-ABI: `threads` host threads with one context/stream
+    each, pulling instances off a shared counter.  Host buffers in, poses out; wall clock, max over ranks."""
     import torch
     import torch.distributed as dist
-    pipe = importlib.import_module("3dvision_b200.pipeline")
-    reg = importlib.import_module("3dvision_b200.registration")
-    reg.Registration.device = dev
     cases = syn.batch_cases(n_instances)
-    insts = [pipe.Instance(reg.PointCloud(c.source), reg.PointCloud(c.target, c.target_normals), reg.FPFHFeatures(c.source_desc),
-                           reg.FPFHFeatures(c.target_desc), c.voxel_size) for c in cases]
+    insts = [dict(source=c.source, target=c.target, target_normals=c.target_normals, source_desc=c.source_desc, target_desc=c.target_desc,
+                  voxel_size=c.voxel_size) for c in cases]
+    pool = b3d.Pool(threads, devices=(dev,))
 
     def run_one(inst):
-        _, f = pipe.process_instance(inst)
-        return f.transformation, f.fitness, f.rmse
-    run_one.run_many = lambda lst: [(f.transformation, f.fitness, f.rmse) for _, f in pipe.register_batch(lst, threads)]
+        (_, _, _), (T, fit, rmse, _) = pool.register([inst])[0]
+        return T, fit, rmse
+    run_one.run_many = lambda lst: [(f[0], f[1], f[2]) for _, f in pool.register(lst)]
 
-    out = bdist.sharded_batch(insts, run_one, device="cuda")            # warm-up: contexts, workspaces, RNG caches
-    secs = []
-    for _ in range(reps):
-        flush.zero_()
-        barrier()
-        t0 = time.perf_counter()
-        out = bdist.sharded_batch(insts, run_one, device="cuda")
-        torch.cuda.synchronize()
-        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        secs.append(float(t.item()))
+    try:
+        out = bdist.sharded_batch(insts, run_one, device="cuda")            # warm-up: contexts, workspaces, RNG caches
+        secs = []
+        for _ in range(reps):
+            flush.zero_()
+            barrier()
+            t0 = time.perf_counter()
+            out = bdist.sharded_batch(insts, run_one, device="cuda")
+            torch.cuda.synchronize()
+            t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            secs.append(float(t.item()))
+    finally:
+        pool.close()
     s = float(np.median(secs))
-    return {"workload": f"configs[3]: {n_instances} instances (30k scene points vs 2k-10k model points each), ransacRegistration(H=100000, "
-                        f"conf 0.999) + icpRefine(thr 0.4*voxel, <=200 it), instance i -> rank i mod {world}, {threads} worker contexts per rank",
-            "registrations_per_s": n_instances / s, "ms_per_batch": 1e3 * s, "n_gpus": world,
-            "min_icp_fitness": float(min(o[1] for o in out)),
-            "max_rot_err_vs_truth": float(max(syn.rotation_error(o[0], c.T_true) for o, c in zip(out, cases))),
-            "max_trans_err_vs_truth": float(max(syn.translation_error(o[0], c.T_true) for o, c in zip(out, cases)))}
+    res = {"workload": f"configs[3]: {n_instances} instances (30k scene points vs 2k-10k model points each), ransacRegistration(H=100000, "
+                       f"conf 0.999) + icpRefine(thr 0.4*voxel, <=200 it), instance i -> rank i mod {world}, b3d_pool with {threads} worker contexts per rank",
+           "registrations_per_s": n_instances / s, "ms_per_batch": 1e3 * s, "n_gpus": world,
+           "min_icp_fitness": float(min(o[1] for o in out)),
+           "max_rot_err_vs_truth": float(max(syn.rotation_error(o[0], c.T_true) for o, c in zip(out, cases))),
+           "max_trans_err_vs_truth": float(max(syn.translation_error(o[0], c.T_true) for o, c in zip(out, cases)))}
+    if rank == 0 and world == 1:
+        # the reference's CPU pool on a bounded sample: the oracle port on 2 of the 64 instances with a 2 000-hypothesis budget, one
+        # thread; scoring is linear in the hypothesis count and dominates, ICP (brute-force NN) is timed in full for 2 iterations
+        from oracle import oracle as O
+        t_r = t_i = 0.0
+        for c in cases[:2]:
+            t0 = time.perf_counter(); r = O.ransac_registration(c.source, c.target, c.source_desc, c.target_desc, c.voxel_size, 2000, 2.0); t_r += time.perf_counter() - t0
+            t0 = time.perf_counter(); O.icp(c.source, c.target, c.target_normals, r.transformation, c.voxel_size * 0.4, 2, True, stop_on_convergence=False); t_i += time.perf_counter() - t0
+        per_inst = (t_r / 2) * (100_000 / 2000) + (t_i / 2) / 2 * 5          # H = 100 000 hypotheses; ~5 ICP iterations to converge
+        cores = max(1, min(os.cpu_count() or 1, 8))
+        res["cpu_baseline"] = {"value": cores / per_inst, "unit": "registrations/s", "cores": cores, "kind": "port",
+                               "sample": f"oracle port, one thread, 2 of the {n_instances} instances: matching + 2 000 hypotheses ({t_r / 2:.2f} s each, scaled x50 to "
+                                         f"H = 100 000) + 2 ICP iterations ({t_i / 2:.2f} s, scaled to 5); {per_inst:.0f} s per instance, x {cores} pool threads "
+                                         "(the reference's only parallelism)"}
+    return res
 
 
 def icp_cpu_baseline(ic, n_sample=30_000):

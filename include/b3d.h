@@ -255,6 +255,30 @@ int b3d_icp_run(b3d_ctx* ctx, const float T0_colmajor[16], float distance_thresh
 int b3d_icp_nearest(b3d_ctx* ctx, const float T_colmajor[16], float distance_threshold,
                     uint32_t* out_idx_host, float* out_d2_host);
 
+/* ---- batched multi-object registration: the orchestrator's worker pool ---------------------------------
+ * Pipeline::run pushes one processInstance task per object into a pool of num_threads workers (src/pipeline.cpp:16,
+ * 321-327; include/thread_pool.hpp); b3d_pool is that pool behind the C-ABI: n_workers persistent host threads, each
+ * with its own context on devices[w % n_devices] (n_devices == 0: device 0), so one pool spreads over all the GPUs of a
+ * box.  b3d_pool_register runs ransacRegistration + icpRefine (src/pipeline.cpp:97-129) for every instance and blocks
+ * until all are done; results[i] belongs to items[i] and equals what b3d_ransac + b3d_icp return for it.  Instances are
+ * independent: no collective.  The first non-zero per-instance status is returned (each result carries its own). */
+typedef struct b3d_instance {
+    const float* src_xyz; size_t n_src;                         /* scene instance cloud (source_down) */
+    const float* tgt_xyz; const float* tgt_normals_or_null; size_t n_tgt;   /* model cloud (+ normals) */
+    const float* src_desc; const float* tgt_desc;               /* FPFH, n x 33 */
+    float voxel_size; int ransac_max_iterations; float ransac_confidence;
+    float icp_distance_threshold; int icp_max_iterations; int point_to_plane;
+} b3d_instance;
+typedef struct b3d_instance_result {
+    float coarse_T[16]; float coarse_fitness, coarse_rmse;      /* ransacRegistration */
+    float T[16]; float fitness, rmse; int32_t icp_iterations;   /* icpRefine */
+    int32_t status;                                             /* b3d_status of this instance */
+} b3d_instance_result;
+typedef struct b3d_pool b3d_pool;
+int  b3d_pool_create(int n_workers, const int* devices, int n_devices, b3d_pool** out);
+int  b3d_pool_register(b3d_pool* pool, const b3d_instance* items, size_t n, b3d_instance_result* results);
+void b3d_pool_destroy(b3d_pool* pool);
+
 /* ---- multi-GPU: one process (or host thread) per GPU, NCCL over NVLink --------------------------------
  * The two parts of the path that shard: feature-matching rows (one in-place ncclAllGather of the index slices) and RANSAC
  * hypothesis ids (contiguous ranges; one ncclAllGather of three 64-bit keys per rank, from which every rank resolves the
