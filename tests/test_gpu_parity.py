@@ -398,7 +398,7 @@ def test_ransac_chunked_scoring_stops_where_the_reference_breaks(ctx, oracle):
     """registration.cpp:290: a clean scene exceeds the confidence after a few iterations and the loop breaks.  Scoring runs in
     chunks of hypothesis ids with a device-side exit flag: later chunks do no work, ids behind the exit read -2 (never ran),
     and the result is the reference's."""
-    H = 250_000
+    H = 700_000                                                                # 1.4e10 pair evaluations: two chunks
     c = syn.ransac_case(n_src=20_000, n_tgt=15_000, seed=77, inlier_frac=1.0, noise=0.00005, max_iterations=H)
     corr = np.where(c.true_match >= 0, c.true_match, 0).astype(np.uint32)
     ref = oracle.ransac(c.source, c.target, corr, c.voxel_size, H, 0.5, want_counts=True)
