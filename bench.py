@@ -317,11 +317,23 @@ def run_ours(args):
                  "and re-counts only pairs inside the proven error band with the reference arithmetic, so it retires the "
                  "reference's algorithmic work with fewer issued instructions; counts stay bit-identical (tests)."),
     }
+    bf16_peak = 1386.4
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         roofline["hbm_peak_gbs_measured"] = peaks.get("hbm_gbs")
+        bf16_peak = float(peaks.get("bf16_tflops_sustained") or bf16_peak)
     except Exception:
         pass
+    # second kernel of the step: descriptor matching on the tensor cores (tcgen05 screen GEMM + exact re-score)
+    match_ms = stage_acc[0] / args.steps
+    m_rows = bdist.shard_range(N_SRC, rank, world)
+    match_flops = 2.0 * 33.0 * float(m_rows[1] - m_rows[0]) * float(N_TGT)
+    match_roofline = {"bound": "tensor", "achieved": match_flops / (match_ms * 1e-3) / 1e12, "peak": bf16_peak, "unit": "TFLOP/s",
+                      "frac": match_flops / (match_ms * 1e-3) / 1e12 / bf16_peak, "kernel": "match_tc_kernel (+ packing, seeding, finalize)",
+                      "stage_ms": match_ms,
+                      "note": "useful flops 2*33*rows*Nt (K = 33) over the matching stage's CUDA-event time against the sustained bf16 figure of "
+                              "MEASURED_PEAKS.json; the GEMM issues K' = 112 (hi/lo bf16 split, 3.4x) and its epilogue is TMEM-read bound "
+                              "(every accumulator goes through tcgen05.ld once), DESIGN.md 4.1"}
 
     line = {
         "metric": "ransac_hyp_per_s", "value": value, "unit": "hyp/s", "n_gpus": world, "steps": args.steps,
@@ -333,6 +345,7 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": "hyp/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": int(launches),
         "roofline": roofline,
+        "match_roofline": match_roofline,
         "stages_ms": {"match": stage_acc[0] / args.steps, "prepare": stage_acc[1] / args.steps,
                       "score": stage_acc[2] / args.steps, "select_finish": stage_acc[3] / args.steps},
         "result": {"fitness": result[1], "rmse": result[2], "best_iteration": result[3]},
