@@ -252,6 +252,12 @@ int b3d_icp_exact_sum_stats(b3d_ctx* c, uint32_t out[128]) {
     return B3D_OK;
 }
 
+int b3d_sequential_sum(b3d_ctx* c, const float* terms, size_t n, float* out_sum, uint32_t out_stats[3]) {
+    if (!c || !out_sum || (n && !terms)) return B3D_ERR_INVALID;
+    B3D_CUDA(c, enter(c));
+    return sequential_sum_impl(c, terms, n, out_sum, out_stats);
+}
+
 int b3d_voxel_downsample(b3d_ctx* c, const float* xyz, size_t n, const float* colors_or_null, float voxel_size,
                          float* out_xyz, float* out_colors_or_null, size_t capacity, size_t* out_n) {
     if (!c || !out_n || (n && (!xyz || !out_xyz))) return B3D_ERR_INVALID;

@@ -121,7 +121,7 @@ struct b3d_ctx {
     b3d::DevBuf icp_cache, icp_cache_idx;                    // per query slot: reference position + hold radius^2, and the match it certifies
     b3d::DevBuf seq_rec, seq_match, seq_P, seq_Q, seq_N;            // reference-order sums: per-query records (legacy chain: compacted pairs)
     b3d::DevBuf ess_terms, ess_bsum, ess_guess, ess_summ;           // exact sequential sums (b3d_ess.cuh): terms, fp64 block sums, guesses, summaries
-    bool fin_smem_opt_in = false, tc_smem_opt_in = false;
+    bool fin_smem_opt_in = false, tc_smem_opt_in = false, seq_smem_opt_in = false;
     int finish_mode = 0;                                     // RANSAC rmse: 0 parallel exact sum (b3d_ess.cuh), 1 one dependent add chain
     bool ess_smem_opt_in = false;                            // cudaFuncSetAttribute done on this context's device
     int icp_mode = 0;                                        // 0 / 2: sums in the reference's order (exact, parallel); 1: fp64 tree sums; 3: legacy one-chain replay
@@ -192,6 +192,7 @@ int ransac_generate_impl(b3d_ctx* c, int h0, int h1);
 int ransac_score_impl(b3d_ctx* c, int h0, int h1);
 int ransac_reduce_impl(b3d_ctx* c, int h0, int h1, const int64_t* limit_key_dev, int64_t* keys_dev);
 int ransac_finish_impl(b3d_ctx* c, const int64_t* keys_dev, float* T, float* fitness, float* rmse, int32_t* best);
+int sequential_sum_impl(b3d_ctx* c, const float* terms_host, size_t n_terms, float* out_sum, uint32_t* out_stats);
 int ransac_reduce3_impl(b3d_ctx* c, int h0, int h1, unsigned long long* keys3_dev);
 int comm_destroy_impl(b3d_ctx* c);
 int ransac_sharded_resident_impl(b3d_ctx* c, float voxel, int H, float confidence, int match, float* T, float* fitness, float* rmse, int32_t* best);

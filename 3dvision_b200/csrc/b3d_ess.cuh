@@ -150,7 +150,10 @@ B3D_HD BlockSummary block_summary(const float* x, int m, float guess, unsigned t
     if (!(dmin > (double)kMarginSlack) || !(dmin < 1e9)) return r;
     int e0 = 0, e1 = 0, e2 = 0, e3 = 0;
     if (!to_units(f2u(s0), tag, e0) || !to_units(f2u(s1), tag, e1) || !to_units(f2u(s2), tag, e2) || !to_units(f2u(s3), tag, e3)) return r;
-    r.Vg = Vg; r.tag = tag; r.margin = (int)dmin - kMarginSlack;
+    const int margin = (int)dmin - kMarginSlack;
+    if (margin < 1) return r;                                    // 8 < dmin < 9: no start offset is covered (and the walk's one-compare
+                                                                 // range test |d| < margin, done on unsigned values, needs margin >= 1)
+    r.Vg = Vg; r.tag = tag; r.margin = margin;
     r.o[0] = e0 - Vg; r.o[1] = upper ? 0 : e1 - Vg - 1; r.o[2] = e2 - Vg - 2; r.o[3] = upper ? 0 : e3 - Vg - 3;
     return r;
 }

@@ -818,6 +818,23 @@ finish_tail_kernel(const float* __restrict__ terms, const ess::BlockSummary* __r
     out[18] = __int_as_float(st->fin_id);
 }
 
+// Diagnostic (b3d_sequential_sum): the exact-sum passes over caller-supplied terms, so the machinery the rmse and ICP sums
+// ride on can be checked directly against `for (x : terms) s += x` on adversarial inputs (ties, cancellation, binade
+// crossings, zeros, denormals, non-finite terms).
+struct LoadTerms {
+    const float* x;
+    __device__ __forceinline__ bool operator()(unsigned i, float (&t)[1]) const { t[0] = x[i]; return true; }
+};
+__global__ void __launch_bounds__(ess::kChainThreads)
+sequential_sum_tail_kernel(const float* __restrict__ terms, const ess::BlockSummary* __restrict__ summ, unsigned n, DeviceState* __restrict__ st) {
+    extern __shared__ __align__(128) unsigned char ess_smem[];
+    ess::ChainSmem& sm = *reinterpret_cast<ess::ChainSmem*>(ess_smem);
+    if (threadIdx.x < 4) st->ess_stats[0][threadIdx.x] = 0u;
+    __syncwarp();
+    const float total = ess::chain(terms, summ, n, sm, st->ess_stats[0]);
+    if (threadIdx.x == 0) st->ess_sums[0] = total;
+}
+
 // ---------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------
@@ -1182,6 +1199,39 @@ int ransac_finish_impl(b3d_ctx* c, const int64_t* keys_dev, float* T, float* fit
     *rmse = c->h_state->out18[17];
     int32_t id; memcpy(&id, &c->h_state->out18[18], sizeof(id));
     if (best) *best = id;
+    return B3D_OK;
+}
+
+int sequential_sum_impl(b3d_ctx* c, const float* terms_host, size_t n_terms, float* out_sum, uint32_t* out_stats) {
+    if (n_terms > 0x7fffffffull) return fail(c, B3D_ERR_INVALID, "sequential_sum: too many terms");
+    DeviceState* st = c->state.as<DeviceState>();
+    const unsigned n = (unsigned)n_terms;
+    if (n == 0) { *out_sum = 0.0f; if (out_stats) { out_stats[0] = out_stats[1] = out_stats[2] = 0u; } return B3D_OK; }
+    const size_t stride = ess::padded_terms(n);
+    B3D_CUDA(c, c->ess_terms.ensure(sizeof(float) * stride));
+    B3D_CUDA(c, c->ess_bsum.ensure(sizeof(double) * (stride / ess::kBlock)));
+    B3D_CUDA(c, c->ess_guess.ensure(sizeof(double) * (stride / ess::kSuperTerms)));
+    B3D_CUDA(c, c->ess_summ.ensure(sizeof(ess::BlockSummary) * (stride / ess::kBlock)));
+    if (!c->seq_smem_opt_in) {
+        B3D_CUDA(c, cudaFuncSetAttribute(sequential_sum_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ess::ChainSmem)));
+        c->seq_smem_opt_in = true;
+    }
+    float* terms = c->ess_terms.as<float>();
+    B3D_CUDA(c, cudaMemcpyAsync(terms, terms_host, sizeof(float) * n, cudaMemcpyHostToDevice, c->stream));
+    LoadTerms fn{terms};                                     // in place: every thread reads its own element before storing it
+    const int term_blocks = div_up(n, ess::kTermsThreads);
+    ess::terms_kernel<1><<<term_blocks, ess::kTermsThreads, 0, c->stream>>>(fn, n, nullptr, terms, stride, c->ess_bsum.as<double>(), c->ess_guess.as<double>(), nullptr);
+    B3D_LAUNCHED(c);
+    ess::summary_kernel<<<dim3((unsigned)div_up(term_blocks, ess::kSummaryWarps), 1), ess::kSummaryWarps * 32, 0, c->stream>>>(
+        terms, stride, c->ess_bsum.as<double>(), c->ess_guess.as<double>(), n, nullptr, c->ess_summ.as<ess::BlockSummary>());
+    B3D_LAUNCHED(c);
+    sequential_sum_tail_kernel<<<1, ess::kChainThreads, sizeof(ess::ChainSmem), c->stream>>>(terms, c->ess_summ.as<ess::BlockSummary>(), n, st);
+    B3D_LAUNCHED(c);
+    uint32_t stats[4];
+    B3D_CUDA(c, cudaMemcpyAsync(out_sum, &st->ess_sums[0], sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    B3D_CUDA(c, cudaMemcpyAsync(stats, st->ess_stats[0], sizeof(stats), cudaMemcpyDeviceToHost, c->stream));
+    B3D_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (out_stats) { out_stats[0] = stats[0]; out_stats[1] = stats[1]; out_stats[2] = stats[2]; }
     return B3D_OK;
 }
 

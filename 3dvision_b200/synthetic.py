@@ -167,3 +167,35 @@ def rotation_error(Ta, Tb) -> float:
 def translation_error(Ta, Tb) -> float:
     """Euclidean norm of the translation difference in metres (north_star tolerance: 1e-6)."""
     return float(np.linalg.norm(np.asarray(Ta, np.float64)[:3, 3] - np.asarray(Tb, np.float64)[:3, 3]))
+
+
+def adversarial_terms(rng) -> np.ndarray:
+    """A term sequence for the exact-sequential-sum checks (csrc/b3d_ess.cuh): up to 15 stretches of different character —
+    zeros, squared-distance-like positives, signed noise over 15 decades, constant powers of two (ties), mirrored walks that
+    return to the start, per-term random magnitudes, sparse hits among zeros, integer grids — each handing the next a
+    running sum it was not summarised for.  Seeded, so a failing case is a seed."""
+    parts = []
+    for _ in range(int(rng.integers(1, 16))):
+        m = int(rng.integers(1, 40_000))
+        kind = int(rng.integers(0, 8))
+        if kind == 0:
+            p = np.zeros(m, np.float32)
+        elif kind == 1:
+            p = (rng.random(m, dtype=np.float32) ** 2) * np.float32(10.0 ** rng.integers(-10, 3))
+        elif kind == 2:
+            p = rng.standard_normal(m).astype(np.float32) * np.float32(10.0 ** rng.integers(-10, 5))
+        elif kind == 3:
+            p = np.full(m, np.float32(2.0 ** int(rng.integers(-28, 3))) * np.float32(rng.choice([1.0, -1.0, 1.5, 3.0])), np.float32)
+        elif kind == 4:
+            h = rng.standard_normal(m).astype(np.float32) * np.float32(10.0 ** rng.integers(-4, 3))
+            p = np.concatenate([h, -h[::-1]])
+        elif kind == 5:
+            p = rng.standard_normal(m).astype(np.float32) * (np.float32(10.0) ** rng.integers(-12, 6, m).astype(np.float32))
+        elif kind == 6:
+            p = np.zeros(m, np.float32)
+            hit = rng.random(m) < 10.0 ** rng.uniform(-3.5, -0.5)
+            p[hit] = rng.standard_normal(int(hit.sum())).astype(np.float32) * np.float32(10.0 ** rng.integers(-6, 1))
+        else:
+            p = rng.integers(-4, 5, m).astype(np.float32) * np.float32(2.0 ** int(rng.integers(-6, 20)))
+        parts.append(p)
+    return np.concatenate(parts)

@@ -329,6 +329,12 @@ int b3d_score_recounts(b3d_ctx* ctx, uint64_t* out_groups);
  * 0-6 and 16-24: the two point-to-point passes). */
 int b3d_icp_exact_sum_stats(b3d_ctx* ctx, uint32_t out[128]);
 
+/* Diagnostic: the fp32 value of `float s = 0; for (i < n) s += terms[i];` (the accumulation loops of
+ * src/registration.cpp:277 `total_error += err * err` and :351-357 / :377-391, whose order the default modes keep), computed by
+ * the same parallel exact-sum passes those paths use (b3d_ess.cuh) — so they can be checked on arbitrary, adversarial term
+ * sequences. terms: host, n floats. out_stats (may be NULL): walk rounds, 32-term blocks added term by term, SM cycles / 16. */
+int b3d_sequential_sum(b3d_ctx* ctx, const float* terms, size_t n, float* out_sum, uint32_t out_stats[3]);
+
 /* Measures the sustained issue rate of separate (un-fused) FMUL + FADD instructions on this
  * device, in lane-operations per second: the roofline denominator of the scoring kernel, whose
  * arithmetic must not be contracted into FMAs (reference build: no FMA, README.md:13). */

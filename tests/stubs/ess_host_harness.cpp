@@ -116,3 +116,21 @@ extern "C" float ess_parallel_sum(const float* x, long n, long* stats) {
     if (stats) { stats[0] = st[0]; stats[1] = st[1]; stats[2] = st[2]; }
     return s;
 }
+
+// Smallest margin over the usable block summaries of x (both frames, guesses = the fp64 running sum), or a large number if none.
+extern "C" long ess_min_usable_margin(const float* x, long n) {
+    const long nb = (n + kBlock - 1) / kBlock;
+    double run = 0.0;
+    long least = 1L << 40;
+    for (long b = 0; b < nb; ++b) {
+        const long m = (n - b * kBlock) < kBlock ? (n - b * kBlock) : kBlock;
+        const float g = (float)run;
+        const unsigned tags[2] = {frame_of(g), other_frame_of(g)};
+        for (unsigned tag : tags) {
+            const BlockSummary r = block_summary(x + b * kBlock, (int)m, g, tag);
+            if (!(r.tag & kFail) && r.margin < least) least = r.margin;
+        }
+        for (long i = 0; i < m; ++i) run += (double)x[b * kBlock + i];
+    }
+    return least;
+}

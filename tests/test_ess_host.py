@@ -26,6 +26,8 @@ def ess(tmp_path_factory):
     lib.ess_seq_sum.argtypes = [fp, ctypes.c_long]
     lib.ess_parallel_sum.restype = ctypes.c_float
     lib.ess_parallel_sum.argtypes = [fp, ctypes.c_long, ctypes.POINTER(ctypes.c_long)]
+    lib.ess_min_usable_margin.restype = ctypes.c_long
+    lib.ess_min_usable_margin.argtypes = [fp, ctypes.c_long]
     return lib
 
 
@@ -177,3 +179,27 @@ def test_leading_and_embedded_zero_runs(ess):
     x = np.concatenate([h, -h[::-1], np.zeros(5000, np.float32), h])
     a, b, _ = _both(ess, x)
     assert _same_bits(a, b)
+
+
+# Seeds of synthetic.adversarial_terms that a 60 000-case soak of the device passes found (scripts/fuzz_exact_sums.py): a block
+# whose partial sums come within (8, 9) units of a frame border got margin 0, and the walk's unsigned one-compare range test
+# accepted it for every offset.  block_summary() now rejects margin < 1.
+SOAK_FINDS = [55067, 55824, 56985, 59046, 61030]
+
+
+@pytest.mark.parametrize("seed", SOAK_FINDS + list(range(40)))
+def test_adversarial_sequences(ess, seed):
+    import importlib
+    syn = importlib.import_module("3dvision_b200.synthetic")
+    x = syn.adversarial_terms(np.random.default_rng(seed))
+    a, b, _ = _both(ess, x)
+    assert _same_bits(a, b)
+
+
+def test_margin_is_never_zero_on_a_usable_block(ess):
+    """A usable summary must cover at least the exact guess: margin >= 1 whenever the tag is not kFail."""
+    import importlib
+    syn = importlib.import_module("3dvision_b200.synthetic")
+    for seed in SOAK_FINDS:
+        x = np.ascontiguousarray(syn.adversarial_terms(np.random.default_rng(seed)), np.float32)
+        assert ess.ess_min_usable_margin(x.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), x.size) >= 1
