@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libb3d.so")
 SOURCES = ["b3d_api.cu", "b3d_match.cu", "b3d_match_tc.cu", "b3d_ransac.cu", "b3d_icp.cu", "b3d_features.cu", "b3d_pose.cu", "b3d_dist.cu", "b3d_pool.cu"]
-HEADERS = ["b3d_common.cuh", "b3d_linalg.cuh", "b3d_scan.cuh", "b3d_grid.cuh", "b3d_featmath.cuh", "b3d_ess.cuh", os.path.join("..", "..", "include", "b3d.h")]
+HEADERS = ["b3d_common.cuh", "b3d_linalg.cuh", "b3d_scan.cuh", "b3d_grid.cuh", "b3d_featmath.cuh", "b3d_ess.cuh", "b3d_libm.cuh", os.path.join("..", "..", "include", "b3d.h")]
 
 # --fmad=false: the reference CPU build never contracts a*b+c (README.md:13, no -march), and
 # bit-exact inlier counts / match indices depend on it.  Kernels that may fuse say so with

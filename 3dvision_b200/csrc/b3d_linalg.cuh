@@ -16,6 +16,8 @@
 #include <float.h>
 #include <math.h>
 
+#include "b3d_libm.cuh"
+
 #define B3D_HD __host__ __device__ __forceinline__
 
 namespace b3d {
@@ -320,10 +322,11 @@ B3D_HD Quat quat_mul(Quat a, Quat b) {
 }
 B3D_HD void euler_xyz_to_matrix(float ax, float ay, float az, Mat3& R) {
     float hx = 0.5f * ax, hy = 0.5f * ay, hz = 0.5f * az;
-    float sx = sinf(hx), sy = sinf(hy), sz = sinf(hz);
-    Quat qx{cosf(hx), sx * 1.0f, sx * 0.0f, sx * 0.0f};
-    Quat qy{cosf(hy), sy * 0.0f, sy * 1.0f, sy * 0.0f};
-    Quat qz{cosf(hz), sz * 0.0f, sz * 0.0f, sz * 1.0f};
+    // std::sin / std::cos of the reference are glibc's sinf / cosf, not CUDA's (b3d_libm.cuh)
+    float sx = libm::sin_libm(hx), sy = libm::sin_libm(hy), sz = libm::sin_libm(hz);
+    Quat qx{libm::cos_libm(hx), sx * 1.0f, sx * 0.0f, sx * 0.0f};
+    Quat qy{libm::cos_libm(hy), sy * 0.0f, sy * 1.0f, sy * 0.0f};
+    Quat qz{libm::cos_libm(hz), sz * 0.0f, sz * 0.0f, sz * 1.0f};
     Quat q = quat_mul(quat_mul(qx, qy), qz);
     float tx = 2.0f * q.x, ty = 2.0f * q.y, tz = 2.0f * q.z;
     float twx = tx * q.w, twy = ty * q.w, twz = tz * q.w;

@@ -199,3 +199,32 @@ def adversarial_terms(rng) -> np.ndarray:
             p = rng.integers(-4, 5, m).astype(np.float32) * np.float32(2.0 ** int(rng.integers(-6, 20)))
         parts.append(p)
     return np.concatenate(parts)
+
+
+def random_icp_case(seed):
+    """One case of the ICP soak (scripts/fuzz_registration.py): random sizes, noise, threshold, start pose, iteration cap
+    and error metric.  Returns (IcpCase, point_to_plane).  Tight thresholds leave a handful of correspondences, so the
+    6x6 system is singular and the update angles are large — the cases that exposed CUDA-vs-glibc sinf / cosf."""
+    rng = np.random.default_rng(seed)
+    n_model = int(rng.integers(40, 6000))
+    n_scene = int(rng.integers(40, 12000))
+    noise = float(10.0 ** rng.uniform(-4.5, -2.5))
+    thr = float(10.0 ** rng.uniform(-3.3, -1.7))
+    iters = int(rng.choice([1, 2, 3, 5, 10, 30, 60]))
+    plane = bool(rng.integers(0, 2))
+    c = icp_case(n_model=n_model, n_scene=n_scene, seed=seed, noise=noise, threshold=thr, iterations=iters,
+                 init_angle_deg=float(rng.uniform(0.0, 4.0)), init_shift=float(rng.uniform(0.0, 0.006)))
+    return c, plane
+
+
+def random_ransac_case(seed):
+    """One case of the ransacRegistration soak: random sizes, inlier ratio, voxel, noise, hypothesis count, confidence.
+    Returns (RansacCase, confidence)."""
+    rng = np.random.default_rng(seed)
+    n_src = int(rng.integers(30, 5000))
+    n_tgt = int(rng.integers(30, 5000))
+    H = int(rng.choice([1, 10, 300, 1000, 4000]))
+    conf = float(rng.choice([0.05, 0.5, 0.999, 2.0]))
+    c = ransac_case(n_src=n_src, n_tgt=n_tgt, seed=seed, inlier_frac=float(rng.uniform(0.05, 0.95)),
+                    voxel=float(10.0 ** rng.uniform(-3.3, -2.0)), noise=float(10.0 ** rng.uniform(-4.5, -3.0)), max_iterations=H)
+    return c, conf
