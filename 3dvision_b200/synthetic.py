@@ -228,3 +228,70 @@ def random_ransac_case(seed):
     c = ransac_case(n_src=n_src, n_tgt=n_tgt, seed=seed, inlier_frac=float(rng.uniform(0.05, 0.95)),
                     voxel=float(10.0 ** rng.uniform(-3.3, -2.0)), noise=float(10.0 ** rng.uniform(-4.5, -3.0)), max_iterations=H)
     return c, conf
+
+
+def random_cloud(seed):
+    """One cloud of the front-end soak (scripts/fuzz_features.py): a random shape (surface, box, clusters with exact
+    duplicates, plane, line, lattice — the degenerate ones make the covariance eigen-solver and the Darboux frames hit
+    their edge cases), a random extent, and the stage parameters to run it with.
+    Returns (xyz float32 (n,3), voxel, k, radius)."""
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(1, 4000))
+    extent = float(10.0 ** rng.uniform(-1.5, 0.7))
+    kind = int(rng.integers(0, 7))
+    if kind == 0:
+        xyz, _ = torus(n, rng, R=0.4 * extent, r=0.15 * extent)
+        xyz = xyz + rng.normal(0, 0.002 * extent, xyz.shape)
+    elif kind == 1:
+        xyz = rng.uniform(-extent, extent, (n, 3))
+    elif kind == 2:
+        centres = rng.uniform(-extent, extent, (max(1, n // 40), 3))
+        xyz = centres[rng.integers(0, len(centres), n)] + rng.normal(0, 0.01 * extent, (n, 3))
+        dup = rng.random(n) < 0.2
+        xyz[dup] = xyz[rng.integers(0, n, int(dup.sum()))]
+    elif kind == 3:
+        xyz = np.zeros((n, 3))
+        xyz[:, :2] = rng.uniform(-extent, extent, (n, 2))
+        xyz[:, 2] = 0.25 * extent
+    elif kind == 4:
+        t = rng.uniform(-extent, extent, n)
+        xyz = np.stack([t, 0.5 * t, -0.25 * t], 1)
+    elif kind == 5:
+        side = max(1, int(round(n ** (1.0 / 3.0))))
+        g = np.stack(np.meshgrid(np.arange(side), np.arange(side), np.arange(side), indexing="ij"), -1).reshape(-1, 3)
+        xyz = (g[rng.permutation(len(g))] - side / 2.0) * (2.0 * extent / side)
+    else:
+        xyz = rng.normal(0, extent, (n, 3)) * np.array([1.0, 0.05, 0.001])
+    xyz = np.ascontiguousarray(xyz, np.float32)
+    voxel = float(extent * 10.0 ** rng.uniform(-2.0, -0.3))
+    k = int(rng.choice([3, 5, 10, 30, 30, 30, 64, 128]))
+    radius = float(extent * 10.0 ** rng.uniform(-1.6, 0.3))
+    return xyz, voxel, k, radius
+
+
+def random_descriptors(seed):
+    """Source / target descriptor sets of the matcher soak (scripts/fuzz_match.py): random sizes and a mix of populations
+    — histograms of random sparsity, noisy copies of target rows, exact duplicates inside the target (the lowest index must
+    win, src/registration.cpp:222-229 keeps the first strict minimum), rows scaled far above the rest (wide screen band),
+    all-zero rows.  Returns (source (ns,33), target (nt,33)) float32."""
+    rng = np.random.default_rng(seed)
+    ns, nt = int(rng.integers(1, 3000)), int(rng.integers(1, 3000))
+    td = histograms(nt, rng, sparsity=float(rng.uniform(0.0, 0.9)))
+    if rng.random() < 0.5 and nt > 4:                       # exact duplicates inside the target
+        m = int(rng.integers(1, nt // 2 + 1))
+        td[rng.integers(0, nt, m)] = td[rng.integers(0, nt, m)]
+    if rng.random() < 0.3:                                  # a few rows far from the rest
+        td[rng.integers(0, nt, max(1, nt // 50))] *= np.float32(rng.uniform(3.0, 300.0))
+    if rng.random() < 0.3:
+        td[rng.integers(0, nt, max(1, nt // 100))] = 0.0
+    sd = histograms(ns, rng, sparsity=float(rng.uniform(0.0, 0.9)))
+    near = rng.random(ns) < rng.uniform(0.0, 1.0)           # noisy (or exact) copies of target rows
+    noise = float(10.0 ** rng.uniform(-7.0, -1.5)) if rng.random() < 0.8 else 0.0
+    pick = rng.integers(0, nt, int(near.sum()))
+    sd[near] = np.abs(td[pick] + rng.normal(0, noise, (int(near.sum()), 33))).astype(np.float32)
+    if rng.random() < 0.2:
+        sd[rng.integers(0, ns, max(1, ns // 100))] = 0.0
+    if rng.random() < 0.2:
+        scale = np.float32(10.0 ** rng.uniform(-3.0, 3.0))  # FPFH of this code base sums to ~300 per row, not 1
+        sd, td = sd * scale, td * scale
+    return np.ascontiguousarray(sd, np.float32), np.ascontiguousarray(td, np.float32)

@@ -37,3 +37,39 @@ def test_random_ransac_case_is_bit_identical(ctx, oracle, seed):
     ref = oracle.ransac_registration(c.source, c.target, c.source_desc, c.target_desc, c.voxel_size, H, conf)
     T, fit, rmse = ctx.ransac(c.source, c.target, c.source_desc, c.target_desc, c.voxel_size, H, conf)[:3]
     assert np.array_equal(_bits(T), _bits(ref.transformation)) and _bits(fit) == _bits(ref.fitness) and _bits(rmse) == _bits(ref.rmse)
+
+
+def _same(a, b):
+    a = np.ascontiguousarray(a, np.float32); b = np.ascontiguousarray(b, np.float32)
+    return a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+@pytest.mark.parametrize("seed", range(3000, 3040))
+def test_random_cloud_front_end_is_bit_identical(ctx, oracle, b3d, seed):
+    """scripts/fuzz_features.py: voxelDownsample, estimateNormals, computeFPFH on random (often degenerate) clouds."""
+    xyz, voxel, k, radius = syn.random_cloud(seed)
+    try:
+        down, _ = ctx.voxel_downsample(xyz, voxel)
+    except b3d.B3DError:
+        pytest.skip("|coordinate / voxel| >= 2^20 is refused")
+    want = oracle.voxel_downsample(xyz, voxel)
+    assert _same(down, want)
+    nrm = oracle.estimate_normals(want, k)
+    assert _same(ctx.estimate_normals(want, k), nrm)
+    assert _same(ctx.compute_fpfh(want, nrm, radius), oracle.compute_fpfh(want, nrm, radius))
+
+
+@pytest.mark.parametrize("seed", range(4000, 4040))
+def test_random_descriptor_sets_match_identically_on_both_matchers(ctx, oracle, seed):
+    """scripts/fuzz_match.py: tensor-core screen + exact re-score (mode 2) and the CUDA-core kernel (mode 1)."""
+    sd, td = syn.random_descriptors(seed)
+    want = oracle.match_features(sd, td)
+    ctx.set_clouds(np.zeros((sd.shape[0], 3), np.float32), np.zeros((td.shape[0], 3), np.float32))
+    ctx.set_features(sd, td)
+    try:
+        for mode in (2, 1):
+            ctx.set_match_mode(mode)
+            ctx.match_features()
+            assert np.array_equal(ctx.get_correspondences(), want)
+    finally:
+        ctx.set_match_mode(0)
