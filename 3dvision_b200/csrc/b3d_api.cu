@@ -252,6 +252,21 @@ int b3d_icp_exact_sum_stats(b3d_ctx* c, uint32_t out[128]) {
     return B3D_OK;
 }
 
+int b3d_icp_exact_sum_dump(b3d_ctx* c, float* terms_out, size_t capacity_floats, size_t* out_stride, float sums_out[32]) {
+    if (!c || !out_stride || !sums_out) return B3D_ERR_INVALID;
+    B3D_CUDA(c, enter(c));
+    const size_t stride = (c->n_src + 4095) / 4096 * 4096;             // ess::padded_terms: whole 4096-term chunks
+    *out_stride = stride;
+    B3D_CUDA(c, cudaMemcpyAsync(sums_out, c->state.as<DeviceState>()->ess_sums, sizeof(float) * 32, cudaMemcpyDeviceToHost, c->stream));
+    if (terms_out) {
+        const size_t have = c->ess_terms.cap / sizeof(float);
+        const size_t n = capacity_floats < have ? capacity_floats : have;
+        B3D_CUDA(c, cudaMemcpyAsync(terms_out, c->ess_terms.as<float>(), sizeof(float) * n, cudaMemcpyDeviceToHost, c->stream));
+    }
+    B3D_CUDA(c, cudaStreamSynchronize(c->stream));
+    return B3D_OK;
+}
+
 int b3d_sequential_sum(b3d_ctx* c, const float* terms, size_t n, float* out_sum, uint32_t out_stats[3]) {
     if (!c || !out_sum || (n && !terms)) return B3D_ERR_INVALID;
     B3D_CUDA(c, enter(c));

@@ -291,7 +291,12 @@ static __global__ void __launch_bounds__(kSummaryWarps * 32) summary_kernel(cons
     double inc = own;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { const double o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= (unsigned)d) inc += o; }
-    const float guess = (float)(start + (inc - own)), next_guess = (float)(start + inc);
+    // the block's guess must be the SAME float as its predecessor's next_guess (block_map() ties the two blocks' offsets
+    // through it), so both come from one fp64 expression: an exclusive prefix formed as inc - own can round the other way
+    // at a float tie
+    double excl = __shfl_up_sync(0xffffffffu, inc, 1);
+    if (lane == 0) excl = 0.0;
+    const float guess = (float)(start + excl), next_guess = (float)(start + inc);
     BlockSummary r, r2;
     r.Vg = 0; r.tag = kFail; r.margin = 0; r.pad = 0; r2.Vg = 0; r2.tag = kFail; r2.margin = 0; r2.pad = 0;
 #pragma unroll

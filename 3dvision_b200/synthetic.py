@@ -295,3 +295,65 @@ def random_descriptors(seed):
         scale = np.float32(10.0 ** rng.uniform(-3.0, 3.0))  # FPFH of this code base sums to ~300 per row, not 1
         sd, td = sd * scale, td * scale
     return np.ascontiguousarray(sd, np.float32), np.ascontiguousarray(td, np.float32)
+
+
+def random_scene_case(seed) -> dict:
+    """One case of the whole-pipeline soak (scripts/fuzz_pipeline.py): a model cloud, a scene that is a moved, noisy,
+    sometimes partial / cluttered re-sampling of it (or, rarely, something degenerate), and the parameters of
+    Pipeline::processInstance (src/pipeline.cpp:86-129): voxel, normals k, FPFH radius, RANSAC budget / confidence, ICP
+    threshold / iteration cap / error metric."""
+    rng = np.random.default_rng(seed)
+    n_model, n_scene = int(rng.integers(200, 6000)), int(rng.integers(200, 8000))
+    kind = int(rng.integers(0, 6))
+    if kind <= 2:
+        model = rough_torus(n_model, rng)
+        base = rough_torus(n_scene, rng)
+    elif kind == 3:
+        model, _ = torus(n_model, rng, R=0.25, r=0.09)
+        base, _ = torus(n_scene, rng, R=0.25, r=0.09)
+    elif kind == 4:                                           # a box shell: planar faces, ambiguous registration
+        def shell(n):
+            p = rng.uniform(-0.2, 0.2, (n, 3)); ax = rng.integers(0, 3, n)
+            p[np.arange(n), ax] = np.where(rng.random(n) < 0.5, -0.2, 0.2)
+            return p + np.array([0.0, 0.0, 0.6])
+        model, base = shell(n_model), shell(n_scene)
+    else:                                                     # a flat patch (rank-deficient plane ICP, degenerate normals at the rim)
+        model = np.concatenate([rng.uniform(-0.3, 0.3, (n_model, 2)), np.full((n_model, 1), 0.6)], 1)
+        base = np.concatenate([rng.uniform(-0.3, 0.3, (n_scene, 2)), np.full((n_scene, 1), 0.6)], 1)
+    T = rigid(rng.normal(size=3), float(rng.uniform(0.0, 40.0)), rng.uniform(-0.1, 0.1, 3))
+    scene = apply(np.linalg.inv(T), np.asarray(base, np.float32)) + rng.normal(0, float(10.0 ** rng.uniform(-4.5, -2.5)), (n_scene, 3))
+    if rng.random() < 0.4:                                    # partial view
+        keep = scene[:, int(rng.integers(0, 3))] > np.quantile(scene[:, 0], rng.uniform(0.1, 0.6))
+        if keep.sum() >= 50:
+            scene = scene[keep]
+    if rng.random() < 0.4:                                    # clutter
+        lo, hi = scene.min(0), scene.max(0)
+        scene = np.concatenate([scene, rng.uniform(lo, hi, (int(rng.integers(1, max(2, len(scene) // 3))), 3))])
+    voxel = float(10.0 ** rng.uniform(-2.2, -1.3))
+    return {"model": np.ascontiguousarray(model, np.float32), "scene": np.ascontiguousarray(scene, np.float32), "voxel": voxel,
+            "k": int(rng.choice([5, 10, 30, 30, 60])), "radius": float(voxel * rng.choice([5.0, 5.0, 2.0, 10.0, 0.7])),
+            "H": int(rng.choice([50, 1000, 5000])), "conf": float(rng.choice([0.3, 0.999, 0.999, 2.0])),
+            "icp_thr": float(voxel * rng.choice([0.4, 0.4, 1.0, 3.0])), "icp_iters": int(rng.choice([1, 5, 30, 200])),
+            "plane": bool(rng.random() < 0.7), "T_true": T.astype(np.float32)}
+
+
+def sparse_mixed_terms(rng) -> np.ndarray:
+    """A second family for the exact-sum checks, shaped like the ICP normal-equation terms at a tight threshold: mostly
+    +0 records with a few hits whose magnitudes are drawn PER TERM over many decades (products of coordinates, normals
+    and residuals), both signs.  fp64 prefix sums of such terms are inexact and land on float rounding ties — the case in
+    which a block's guess and its predecessor's next-guess, computed by two different fp64 expressions, once disagreed
+    (found by scripts/fuzz_pipeline.py, seed 856)."""
+    n = int(rng.integers(1, 60_000))
+    x = np.zeros(n, np.float32)
+    density = 10.0 ** rng.uniform(-3.5, 0.0)
+    hit = rng.random(n) < density
+    m = int(hit.sum())
+    lo = int(rng.integers(-14, -2)); hi = lo + int(rng.integers(1, 14))
+    mag = 10.0 ** rng.uniform(lo, hi, m)
+    sign = np.where(rng.random(m) < rng.uniform(0.0, 1.0), -1.0, 1.0)
+    x[hit] = (sign * mag).astype(np.float32)
+    if rng.random() < 0.3 and m:                              # a handful of exact repeats and exact cancellations
+        idx = np.flatnonzero(hit)
+        j = rng.integers(0, m, max(1, m // 10)); k = rng.integers(0, m, max(1, m // 10))
+        x[idx[j]] = x[idx[k]] * np.float32(rng.choice([1.0, -1.0, 0.5, 2.0]))
+    return x

@@ -329,6 +329,11 @@ int b3d_score_recounts(b3d_ctx* ctx, uint64_t* out_groups);
  * 0-6 and 16-24: the two point-to-point passes). */
 int b3d_icp_exact_sum_stats(b3d_ctx* ctx, uint32_t out[128]);
 
+/* Diagnostic: the term arrays terms[v][stride] (v < 28 point-to-plane; stride = n_src rounded up to 4096) the last iteration of the
+ * last reference-order b3d_icp / b3d_icp_run call summed, and the 32 sums it obtained — lets a test re-add them in order on the host.
+ * terms_out may be NULL (sums only); at most capacity_floats floats are copied. */
+int b3d_icp_exact_sum_dump(b3d_ctx* ctx, float* terms_out, size_t capacity_floats, size_t* out_stride, float sums_out[32]);
+
 /* Diagnostic: the fp32 value of `float s = 0; for (i < n) s += terms[i];` (the accumulation loops of
  * src/registration.cpp:277 `total_error += err * err` and :351-357 / :377-391, whose order the default modes keep), computed by
  * the same parallel exact-sum passes those paths use (b3d_ess.cuh) — so they can be checked on arbitrary, adversarial term

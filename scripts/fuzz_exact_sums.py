@@ -17,8 +17,8 @@ def seq(x):
         return np.add.accumulate(x, dtype=np.float32)[-1] if x.size else np.float32(0)
 
 
-def case(rng):
-    return syn.adversarial_terms(rng)
+def case(rng, seed=0):
+    return syn.sparse_mixed_terms(rng) if seed % 2 else syn.adversarial_terms(rng)
 
 
 def main():
@@ -29,7 +29,7 @@ def main():
     total = 0
     with b3d.Context(0) as ctx:
         for s in range(seed0, seed0 + cases):
-            x = case(np.random.default_rng(s))
+            x = case(np.random.default_rng(s), s)
             got, _ = ctx.sequential_sum(x)
             ref = seq(x)
             total += x.size

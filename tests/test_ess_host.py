@@ -26,6 +26,8 @@ def ess(tmp_path_factory):
     lib.ess_seq_sum.argtypes = [fp, ctypes.c_long]
     lib.ess_parallel_sum.restype = ctypes.c_float
     lib.ess_parallel_sum.argtypes = [fp, ctypes.c_long, ctypes.POINTER(ctypes.c_long)]
+    lib.ess_parallel_sum_devicelike.restype = ctypes.c_float
+    lib.ess_parallel_sum_devicelike.argtypes = [fp, ctypes.c_long, ctypes.POINTER(ctypes.c_long)]
     lib.ess_min_usable_margin.restype = ctypes.c_long
     lib.ess_min_usable_margin.argtypes = [fp, ctypes.c_long]
     return lib
@@ -37,6 +39,9 @@ def _both(lib, x):
     st = (ctypes.c_long * 3)()
     a = np.float32(lib.ess_seq_sum(p, x.size))
     b = np.float32(lib.ess_parallel_sum(p, x.size, st))
+    # the lane-by-lane replay of the device passes (fp64 butterflies, Hillis-Steele scan, unit-carrying walk) must agree too
+    c = np.float32(lib.ess_parallel_sum_devicelike(p, x.size, None))
+    assert _same_bits(a, c), (a, c)
     return a, b, tuple(st)
 
 
@@ -203,3 +208,29 @@ def test_margin_is_never_zero_on_a_usable_block(ess):
     for seed in SOAK_FINDS:
         x = np.ascontiguousarray(syn.adversarial_terms(np.random.default_rng(seed)), np.float32)
         assert ess.ess_min_usable_margin(x.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), x.size) >= 1
+
+
+def test_guess_equals_the_predecessors_next_guess(ess):
+    """Sum 9 of the 11th ICP iteration of scripts/fuzz_pipeline.py seed 856 (16 hits in 2068 records): the fp64 prefix after
+    the second hit sits on a float rounding tie, and an exclusive prefix formed as `inclusive - own` rounded the other way
+    than the predecessor's inclusive prefix — the block map then tied two different guesses together and the walk was off
+    by one ulp.  Guess and next-guess now come from the same fp64 expression."""
+    idx = [103, 226, 379, 633, 662, 786, 891, 917, 1242, 1340, 1404, 1497, 1551, 1640, 1694, 2041]
+    val = [2.13406831e-02, 4.87659033e-03, -1.04450270e-12, -1.28960852e-02, -4.93540495e-12, -7.21113978e-13, 1.03771625e-12,
+           2.30799165e-11, 6.08017258e-14, 8.29449818e-02, -1.04637252e-12, 2.15440299e-02, 5.47327101e-04, -2.79879256e-13,
+           1.01686455e-02, -4.61007643e-13]
+    x = np.zeros(2068, np.float32)
+    x[idx] = np.float32(val)
+    a, b, _ = _both(ess, x)
+    assert _same_bits(a, b)
+
+
+@pytest.mark.parametrize("seed", [17383] + list(range(1, 80, 2)))
+def test_sparse_mixed_magnitude_sequences(ess, seed):
+    """synthetic.sparse_mixed_terms: ICP-like sparse hits with per-term magnitudes over many decades; 17383 is the seed a
+    100 000-case soak of the lane-by-lane replay found against the old guess expression."""
+    import importlib
+    syn = importlib.import_module("3dvision_b200.synthetic")
+    x = syn.sparse_mixed_terms(np.random.default_rng(seed))
+    a, b, _ = _both(ess, x)
+    assert _same_bits(a, b)

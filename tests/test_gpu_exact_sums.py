@@ -211,3 +211,25 @@ def test_adversarial_sequences(ctx, seed):
     x = syn.adversarial_terms(np.random.default_rng(seed))
     got, _ = ctx.sequential_sum(x)
     assert _same_bits(got, _seq(x))
+
+
+@pytest.mark.parametrize("seed", [17383] + list(range(501, 700, 2)))
+def test_sparse_mixed_magnitude_sequences(ctx, seed):
+    """ICP-like sparse hits with per-term magnitudes over many decades (synthetic.sparse_mixed_terms); see
+    tests/test_ess_host.py::test_guess_equals_the_predecessors_next_guess for what they are after."""
+    import importlib
+    syn = importlib.import_module("3dvision_b200.synthetic")
+    x = syn.sparse_mixed_terms(np.random.default_rng(seed))
+    got, _ = ctx.sequential_sum(x)
+    assert _same_bits(got, _seq(x))
+
+
+def test_icp_sum_that_sat_on_a_rounding_tie(ctx):
+    idx = [103, 226, 379, 633, 662, 786, 891, 917, 1242, 1340, 1404, 1497, 1551, 1640, 1694, 2041]
+    val = [2.13406831e-02, 4.87659033e-03, -1.04450270e-12, -1.28960852e-02, -4.93540495e-12, -7.21113978e-13, 1.03771625e-12,
+           2.30799165e-11, 6.08017258e-14, 8.29449818e-02, -1.04637252e-12, 2.15440299e-02, 5.47327101e-04, -2.79879256e-13,
+           1.01686455e-02, -4.61007643e-13]
+    x = np.zeros(2068, np.float32)
+    x[idx] = np.float32(val)
+    got, _ = ctx.sequential_sum(x)
+    assert _same_bits(got, _seq(x))

@@ -73,3 +73,25 @@ def test_random_descriptor_sets_match_identically_on_both_matchers(ctx, oracle, 
             assert np.array_equal(ctx.get_correspondences(), want)
     finally:
         ctx.set_match_mode(0)
+
+
+@pytest.mark.parametrize("seed", [856] + list(range(5000, 5030)))
+def test_random_scene_through_the_one_call_pipeline_is_bit_identical(b3d, oracle, seed):
+    """scripts/fuzz_pipeline.py: b3d_prepare_model + b3d_register_scene against the oracle's stage-by-stage chain.  Seed 856
+    is the case whose 11th ICP iteration had a sum on a float rounding tie (tests/test_ess_host.py)."""
+    c = syn.random_scene_case(seed)
+    tgt = oracle.voxel_downsample(c["model"], c["voxel"]); src = oracle.voxel_downsample(c["scene"], c["voxel"])
+    if tgt.shape[0] == 0 or src.shape[0] == 0:
+        pytest.skip("empty after down-sampling")
+    tn = oracle.estimate_normals(tgt, c["k"]); tf = oracle.compute_fpfh(tgt, tn, c["radius"])
+    sn = oracle.estimate_normals(src, c["k"]); sf = oracle.compute_fpfh(src, sn, c["radius"])
+    coarse = oracle.ransac_registration(src, tgt, sf, tf, c["voxel"], c["H"], c["conf"])
+    fine = oracle.icp(src, tgt, tn, coarse.transformation, c["icp_thr"], c["icp_iters"], c["plane"])
+    with b3d.Context(0) as cx:
+        assert cx.prepare_model(c["model"], c["voxel"], c["k"], c["radius"]) == tgt.shape[0]
+        out = cx.register_scene(c["scene"], c["voxel"], c["k"], c["radius"], c["H"], c["conf"], c["icp_thr"], c["icp_iters"], c["plane"])
+    T0, f0, r0, _ = out["coarse"]; T1, f1, r1, it = out["refined"]
+    assert out["n_source_points"] == src.shape[0]
+    assert np.array_equal(_bits(T0), _bits(coarse.transformation)) and _bits(f0) == _bits(coarse.fitness) and _bits(r0) == _bits(coarse.rmse)
+    assert it == fine.extra["iters_run"]
+    assert np.array_equal(_bits(T1), _bits(fine.transformation)) and _bits(f1) == _bits(fine.fitness) and _bits(r1) == _bits(fine.rmse)
