@@ -1,5 +1,6 @@
 """Randomised soak of the stages that feed the hot path (voxelDownsample, estimateNormals, computeFPFH, depth -> cloud)
-against the CPU oracle, through the C-ABI: random clouds incl. degenerate shapes, random voxel / k / radius.
+against the CPU oracle, through the C-ABI: random clouds incl. degenerate shapes, random voxel / k / radius; and of the pose
+post-processing behind it (world poses through Eigen's 4x4 inverse, filterDuplicates).
 Every output must equal the oracle's bit for bit.
 usage: python scripts/fuzz_features.py [cases] [seed0]"""
 import importlib
@@ -70,6 +71,44 @@ def depth_once(ctx, seed):
     return ([] if ok else ["depth_to_cloud"]), f"depth seed {seed}: {h}x{w} mask {None if mask is None else mask.shape} scale {scale} clip {clip:.2f}"
 
 
+def pose_once(ctx, seed):
+    """T_world_object = extrinsics * refined^-1 (Eigen's SSE 4x4 inverse + packet product) and Pipeline::filterDuplicates."""
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(1, 40))
+    Ts = []
+    for _ in range(n):
+        kind = int(rng.integers(0, 5))
+        if kind <= 1:
+            T = syn.rigid(rng.standard_normal(3), float(rng.uniform(-180, 180)), rng.uniform(-2, 2, 3))
+        elif kind == 2:
+            T = rng.standard_normal((4, 4)) * 10.0 ** rng.uniform(-3, 3)                       # general
+        elif kind == 3:
+            T = rng.standard_normal((4, 4)); T[2] = T[0] * rng.uniform(-2, 2) + T[1] * 1e-7 * rng.standard_normal()   # nearly singular
+        else:
+            T = np.diag(10.0 ** rng.uniform(-6, 6, 4)) @ syn.rigid(rng.standard_normal(3), float(rng.uniform(-180, 180)), rng.uniform(-2, 2, 3))
+        Ts.append(np.asarray(T, np.float32))
+    Ts = np.stack(Ts)
+    ext = None if rng.random() < 0.3 else np.asarray(syn.rigid(rng.standard_normal(3), float(rng.uniform(-180, 180)), rng.uniform(-2, 2, 3)), np.float32)
+    bad = []
+    with np.errstate(all="ignore"):
+        got = ctx.world_poses(Ts, ext)
+        for T, g in zip(Ts, got):
+            w = oracle.world_pose(T, ext)
+            if not (np.array_equal(g.view(np.uint32), w.view(np.uint32)) or (np.isnan(g) == np.isnan(w)).all() and np.array_equal(g[~np.isnan(g)], w[~np.isnan(w)])):
+                bad.append("world_pose"); break
+    centres = rng.uniform(-0.5, 0.5, (int(rng.integers(1, 12)), 3))
+    wps = []
+    for _ in range(int(rng.integers(0, 80))):
+        W = np.asarray(syn.rigid(rng.standard_normal(3), float(rng.uniform(-180, 180)), [0, 0, 0]), np.float32)
+        W[:3, 3] = centres[rng.integers(0, len(centres))] + rng.normal(0, 10.0 ** rng.uniform(-4, -1), 3)
+        wps.append(W)
+    min_d = float(rng.choice([0.0, 10.0 ** rng.uniform(-4, 0.5)]))
+    want = oracle.filter_duplicates(wps, min_d); gotw = ctx.filter_duplicates(wps, min_d)
+    if len(want) != len(gotw) or not all(np.array_equal(a, b) for a, b in zip(gotw, want)):
+        bad.append("filter_duplicates")
+    return bad, f"pose seed {seed}: {n} poses, {len(wps)} waypoints, min_distance {min_d:.3e}"
+
+
 def main():
     cases = int(sys.argv[1]) if len(sys.argv) > 1 else 200
     seed0 = int(sys.argv[2]) if len(sys.argv) > 2 else 0
@@ -77,12 +116,12 @@ def main():
     t0 = time.time()
     with b3d.Context(0) as ctx:
         for s in range(seed0, seed0 + cases):
-            for fn in (once, depth_once):
+            for fn in (once, depth_once, pose_once):
                 bad, what = fn(ctx, s)
                 if bad:
                     n_bad += 1
                     print("MISMATCH", bad, what, flush=True)
-    print(f"{cases} clouds + {cases} depth images, {n_bad} mismatching cases, {time.time() - t0:.0f} s")
+    print(f"{cases} clouds + {cases} depth images + {cases} pose sets, {n_bad} mismatching cases, {time.time() - t0:.0f} s")
     sys.exit(1 if n_bad else 0)
 
 
