@@ -234,3 +234,18 @@ def test_sparse_mixed_magnitude_sequences(ess, seed):
     x = syn.sparse_mixed_terms(np.random.default_rng(seed))
     a, b, _ = _both(ess, x)
     assert _same_bits(a, b)
+
+
+def test_lane_by_lane_replay_soak(ess):
+    """2 000 seeded sequences (both families) through the lane-by-lane replay of the device passes; the long soaks
+    (1.6M cases here, 700k on the device) are recorded in DESIGN.md."""
+    import importlib
+    syn = importlib.import_module("3dvision_b200.synthetic")
+    fp = ctypes.POINTER(ctypes.c_float)
+    for seed in range(200_000, 202_000):
+        rng = np.random.default_rng(seed)
+        x = np.ascontiguousarray(syn.sparse_mixed_terms(rng) if seed % 2 else syn.adversarial_terms(rng), np.float32)
+        got = np.float32(ess.ess_parallel_sum_devicelike(x.ctypes.data_as(fp), x.size, None))
+        with np.errstate(all="ignore"):
+            want = np.add.accumulate(x, dtype=np.float32)[-1] if x.size else np.float32(0)
+        assert _same_bits(got, want), seed
