@@ -1,7 +1,7 @@
 """Randomised soak of the tensor-core matcher (screen GEMM + exact re-score, csrc/b3d_match_tc.cu) and the CUDA-core matcher
 against the oracle's nearest-descriptor search (src/registration.cpp:216-232): random sizes and descriptor populations
 (histograms of random sparsity, near-duplicates, exact duplicates -> lowest index must win, scaled outliers, zero rows).
-usage: python scripts/fuzz_match.py [cases] [seed0]"""
+usage: python scripts/fuzz_match.py [cases] [seed0] [large_cases]"""
 import importlib
 import os
 import sys
@@ -36,7 +36,28 @@ def main():
                     w = np.flatnonzero(got != want)
                     print(f"MISMATCH seed {s} mode {mode}: {sd.shape[0]} x {td.shape[0]}, {w.size} rows, first row {w[0]}: got {got[w[0]]} want {want[w[0]]}", flush=True)
             ctx.set_match_mode(0)
-    print(f"{cases} cases x 2 matchers, {bad} mismatches, {time.time() - t0:.0f} s")
+        # large sets, beyond what the CPU oracle finishes quickly: the two device matchers (independent kernels) against each other
+        n_large = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+        for s in range(seed0, seed0 + n_large):
+            rng = np.random.default_rng(10_000_000 + s)
+            ns, nt = int(rng.integers(3000, 60_000)), int(rng.integers(3000, 60_000))
+            td = syn.histograms(nt, rng, sparsity=float(rng.uniform(0.0, 0.9)))
+            sd = syn.histograms(ns, rng, sparsity=float(rng.uniform(0.0, 0.9)))
+            near = rng.random(ns) < rng.uniform(0.0, 1.0)
+            sd[near] = np.abs(td[rng.integers(0, nt, int(near.sum()))] + rng.normal(0, 10.0 ** rng.uniform(-7, -2), (int(near.sum()), 33))).astype(np.float32)
+            if rng.random() < 0.5:
+                td[rng.integers(0, nt, nt // 20)] = td[rng.integers(0, nt, nt // 20)]          # exact duplicates: lowest index wins
+            if rng.random() < 0.3:
+                td[rng.integers(0, nt, 20)] *= np.float32(rng.uniform(3.0, 300.0))
+            ctx.set_clouds(np.zeros((ns, 3), np.float32), np.zeros((nt, 3), np.float32)); ctx.set_features(sd, td)
+            out = []
+            for mode in (2, 1):
+                ctx.set_match_mode(mode); ctx.match_features(); out.append(ctx.get_correspondences())
+            ctx.set_match_mode(0)
+            if not np.array_equal(out[0], out[1]):
+                bad += 1
+                print(f"MISMATCH large seed {s}: {ns} x {nt}: {int((out[0] != out[1]).sum())} rows", flush=True)
+    print(f"{cases} cases x 2 matchers vs oracle + {n_large} large cases matcher vs matcher, {bad} mismatches, {time.time() - t0:.0f} s")
     sys.exit(1 if bad else 0)
 
 
