@@ -32,7 +32,7 @@ SYMBOLS = [
     "b3d_set_clouds", "b3d_set_features", "b3d_set_match_mode", "b3d_match_features", "b3d_get_correspondences", "b3d_get_correspondences_dev", "b3d_set_correspondences",
     "b3d_correspondences_devptr", "b3d_set_score_mode", "b3d_ransac_prepare", "b3d_ransac_score", "b3d_ransac_reduce", "b3d_ransac_reduce3", "b3d_ransac_finish", "b3d_set_finish_mode",
     "b3d_ransac_counts", "b3d_ransac_hypotheses", "b3d_set_icp_mode", "b3d_icp_run", "b3d_icp_nearest",
-    "b3d_kernel_launches", "b3d_stage_ms", "b3d_measure_fp32_rate", "b3d_score_recounts", "b3d_icp_exact_sum_stats", "b3d_sequential_sum", "b3d_icp_exact_sum_dump",
+    "b3d_kernel_launches", "b3d_stage_ms", "b3d_measure_fp32_rate", "b3d_score_recounts", "b3d_icp_exact_sum_stats", "b3d_sequential_sum", "b3d_icp_exact_sum_dump", "b3d_euler_rotations",
     "b3d_prepare_model", "b3d_register_scene", "b3d_register_scene_device", "b3d_depth_to_cloud", "b3d_register_depth", "b3d_world_poses", "b3d_filter_duplicates", "b3d_voxel_downsample", "b3d_estimate_normals", "b3d_compute_fpfh",
 ]
 
@@ -128,6 +128,7 @@ def _declare(L):
     L.b3d_score_recounts.argtypes = [_vp, C.POINTER(C.c_uint64)]
     L.b3d_icp_exact_sum_stats.argtypes = [_vp, C.POINTER(C.c_uint32)]
     L.b3d_icp_exact_sum_dump.argtypes = [_vp, _fp, C.c_size_t, C.POINTER(C.c_size_t), _fp]
+    L.b3d_euler_rotations.argtypes = [_vp, _fp, C.c_size_t, _fp]
     L.b3d_sequential_sum.argtypes = [_vp, _fp, C.c_size_t, C.POINTER(C.c_float), C.POINTER(C.c_uint32)]
     L.b3d_voxel_downsample.argtypes = [_vp, _vp, C.c_size_t, _vp, C.c_float, _vp, _vp, C.c_size_t, C.POINTER(C.c_size_t)]
     L.b3d_depth_to_cloud.argtypes = [_vp, _vp, C.c_int, C.c_int, _vp, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
@@ -300,6 +301,14 @@ class Context:
         terms = np.zeros((n_sums, stride.value), np.float32)
         self._check(self._L.b3d_icp_exact_sum_dump(self._h, terms.ctypes.data_as(_fp), terms.size, C.byref(stride), sums.ctypes.data_as(_fp)))
         return terms, sums
+
+    def euler_rotations(self, angles_xyz) -> np.ndarray:
+        """(n, 3) angles -> (n, 3, 3) Rx(a) Ry(b) Rz(g) as the ICP update forms it (registration.cpp:369-371), on the device."""
+        a = np.ascontiguousarray(angles_xyz, np.float32).reshape(-1, 3)
+        out = np.empty((a.shape[0], 3, 3), np.float32)
+        self._check(self._L.b3d_euler_rotations(self._h, a.ctypes.data_as(_fp) if a.size else None, a.shape[0],
+                                                out.ctypes.data_as(_fp) if a.size else None))
+        return out
 
     def sequential_sum(self, terms: np.ndarray):
         """fp32 `s = 0; for x in terms: s += x` through the device's exact-sum passes; returns (sum, stats[3])."""

@@ -267,6 +267,12 @@ int b3d_icp_exact_sum_dump(b3d_ctx* c, float* terms_out, size_t capacity_floats,
     return B3D_OK;
 }
 
+int b3d_euler_rotations(b3d_ctx* c, const float* angles_xyz, size_t n, float* out_R_rowmajor) {
+    if (!c || (n && (!angles_xyz || !out_R_rowmajor))) return B3D_ERR_INVALID;
+    B3D_CUDA(c, enter(c));
+    return euler_rotations_impl(c, angles_xyz, n, out_R_rowmajor);
+}
+
 int b3d_sequential_sum(b3d_ctx* c, const float* terms, size_t n, float* out_sum, uint32_t out_stats[3]) {
     if (!c || !out_sum || (n && !terms)) return B3D_ERR_INVALID;
     B3D_CUDA(c, enter(c));

@@ -208,6 +208,7 @@ int estimate_normals_impl(b3d_ctx* c, const float* xyz, size_t n, int k, float* 
 int compute_fpfh_impl(b3d_ctx* c, const float* xyz, const float* normals, size_t n, float radius, float* out_desc);
 int world_poses_impl(b3d_ctx* c, const float* refined, size_t n, const float* extrinsics_or_null, float* out);
 int filter_duplicates_impl(b3d_ctx* c, const float* poses, size_t n, float min_distance, float* out, size_t* out_n);
+int euler_rotations_impl(b3d_ctx* c, const float* angles, size_t n, float* out);
 int depth_to_cloud_impl(b3d_ctx* c, const uint16_t* depth, int w, int h, const uint8_t* mask, int mask_w, int mask_h, float scale, float clip,
                         float fx, float fy, float cx, float cy, const uint8_t* bgr, float* out_xyz, float* out_rgb, size_t capacity, size_t* out_n);
 int register_depth_impl(b3d_ctx* c, const uint16_t* depth, int w, int h, const uint8_t* mask, int mask_w, int mask_h, float scale, float clip, float fx, float fy,

@@ -117,6 +117,29 @@ int world_poses_impl(b3d_ctx* c, const float* refined, size_t n, const float* ex
     return B3D_OK;
 }
 
+// Diagnostic (b3d_euler_rotations): the ICP update's rotation, AngleAxis(x, X) * AngleAxis(y, Y) * AngleAxis(z, Z) -> matrix
+// (src/registration.cpp:369-371), for caller-supplied angles - the device build of b3d_libm.cuh's sinf / cosf and of the
+// quaternion product, checkable against the oracle on every argument range.
+__global__ void euler_rotations_kernel(const float* __restrict__ angles, unsigned n, float* __restrict__ out) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Mat3 R;
+    euler_xyz_to_matrix(angles[3 * (size_t)i], angles[3 * (size_t)i + 1], angles[3 * (size_t)i + 2], R);
+    for (int r = 0; r < 3; ++r) for (int cc = 0; cc < 3; ++cc) out[9 * (size_t)i + 3 * r + cc] = R(r, cc);
+}
+int euler_rotations_impl(b3d_ctx* c, const float* angles, size_t n, float* out) {
+    if (n == 0) return B3D_OK;
+    if (n > (1u << 26)) return fail(c, B3D_ERR_INVALID, "euler_rotations: too many triples");
+    B3D_CUDA(c, c->stage_a.ensure(sizeof(float) * 3 * n));
+    B3D_CUDA(c, c->stage_b.ensure(sizeof(float) * 9 * n));
+    B3D_CUDA(c, cudaMemcpyAsync(c->stage_a.p, angles, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, c->stream));
+    euler_rotations_kernel<<<div_up((long long)n, 128), 128, 0, c->stream>>>(c->stage_a.as<float>(), (unsigned)n, c->stage_b.as<float>());
+    B3D_LAUNCHED(c);
+    B3D_CUDA(c, cudaMemcpyAsync(out, c->stage_b.p, sizeof(float) * 9 * n, cudaMemcpyDeviceToHost, c->stream));
+    B3D_CUDA(c, cudaStreamSynchronize(c->stream));
+    return B3D_OK;
+}
+
 int filter_duplicates_impl(b3d_ctx* c, const float* poses, size_t n, float min_distance, float* out, size_t* out_n) {
     *out_n = 0;
     if (n == 0) return B3D_OK;

@@ -329,6 +329,11 @@ int b3d_score_recounts(b3d_ctx* ctx, uint64_t* out_groups);
  * 0-6 and 16-24: the two point-to-point passes). */
 int b3d_icp_exact_sum_stats(b3d_ctx* ctx, uint32_t out[128]);
 
+/* Diagnostic: R = AngleAxis(x, UnitX) * AngleAxis(y, UnitY) * AngleAxis(z, UnitZ) as a matrix, the rotation of the ICP update
+ * (src/registration.cpp:369-371), for n caller-supplied angle triples (host, [n][3]) -> out_R_rowmajor (host, [n][9]). Exercises the
+ * device build of glibc's sinf / cosf (csrc/b3d_libm.cuh) and of Eigen's quaternion product on arbitrary arguments. */
+int b3d_euler_rotations(b3d_ctx* ctx, const float* angles_xyz, size_t n, float* out_R_rowmajor);
+
 /* Diagnostic: the term arrays terms[v][stride] (v < 28 point-to-plane; stride = n_src rounded up to 4096) the last iteration of the
  * last reference-order b3d_icp / b3d_icp_run call summed, and the 32 sums it obtained — lets a test re-add them in order on the host.
  * terms_out may be NULL (sums only); at most capacity_floats floats are copied. */
