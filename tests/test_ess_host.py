@@ -238,7 +238,7 @@ def test_sparse_mixed_magnitude_sequences(ess, seed):
 
 def test_lane_by_lane_replay_soak(ess):
     """2 000 seeded sequences (both families) through the lane-by-lane replay of the device passes; the long soaks
-    (1.6M cases here, 700k on the device) are recorded in DESIGN.md."""
+    (3.6M cases here, 700k on the device) are recorded in DESIGN.md."""
     import importlib
     syn = importlib.import_module("3dvision_b200.synthetic")
     fp = ctypes.POINTER(ctypes.c_float)
